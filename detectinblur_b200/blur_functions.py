@@ -1,0 +1,230 @@
+"""Mirror of the reference's ``models/blur_functions.py`` over the B200 kernels (libdib.so).
+
+Same call signatures and semantics as /root/reference/models/blur_functions.py:
+  * ``manual_blur(image_GPU, psf_GPU, add_noise, noise_level, add_block, add_jpeg_artifact, jpeg_compressor)``  (:11-89)
+  * ``blur_image_list(images_GPU, blur_dicts, psfs_GPU, ...)`` mutating the list in place                         (:92-100)
+plus ``blur_batch`` -- the batched call both are built on (one tap compaction launch + one or two blur launches
+for the whole list instead of O(taps) launches and two host syncs per tap per image).
+
+Differences from the reference, all deliberate:
+  * results are new contiguous tensors (the reference returns a crop view of its padded accumulator);
+  * CUDA tensors only: there is no CPU path;
+  * fp32 images take the tiled kernel (FMA accumulation, <= 1e-5 from the reference loop; measured ~3e-7);
+    ``exact=True`` (or ``DIB_EXACT=1``) forces the exact-order kernel, bit-identical to the reference's loop.
+    fp16 images always take the exact-order kernel, bit-identical to the reference's half loop.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import psf_ops
+
+_DT = {torch.float32: _lib.DIB_F32, torch.float16: _lib.DIB_F16}
+_launch_count = 0     # kernels launched by this module (bench.py reads it for "gpu_launches")
+
+
+def launch_count():
+    return _launch_count
+
+
+def _exact_default():
+    return os.environ.get("DIB_EXACT", "0") not in ("0", "", "false", "False")
+
+
+def pad_mode_for(psf_side, H, W):
+    """Boundary mode manual_blur uses -- blur_functions.py:17 (256 branch), :55-58 (zeros below 64, else reflect).
+
+    Raises RuntimeError where the reference does: torch's reflect padding needs pad (64) < dim."""
+    if psf_side > 129:
+        return _lib.PAD_REPLICATE256
+    if H < 64 or W < 64:
+        return _lib.PAD_ZERO128
+    if H <= 64 or W <= 64:
+        raise RuntimeError("Argument #4: Padding size should be less than the corresponding input dimension, "
+                           "but got: padding (63, 64) at dimension 2 of input %s" % ([1, -1, H, W],))
+    return _lib.PAD_REFLECT128
+
+
+def blur_batch(images, tapset, psf_indices, outs=None, noise=None, noise_sd=None, clamp=None, philox_seed=None,
+               mean=None, std=None, gamma=None, exact=None):
+    """Blur a list of CHW CUDA tensors (same dtype, any sizes) with PSFs of ``tapset``.
+
+    images       list of [C, H, W] tensors (float32 or float16, rows contiguous)
+    psf_indices  per image: index into ``tapset`` or -1 (pass the image through the epilogue only)
+    outs         optional list of destination tensors ([C, H, W'] with W' >= W allowed: pitched / padded batches)
+    noise        optional list of pre-drawn N(0,1) tensors (or None entries), ``noise_sd`` the matching sqrt(var)
+    philox_seed  draw the noise in-kernel instead (Philox4x32-10); needs ``noise_sd``
+    mean, std    optional per-image (C,) sequences: fused ``(x - mean) / std`` (net_transforms.py:135-139)
+    Returns the list of output tensors.
+    """
+    global _launch_count
+    n = len(images)
+    if n == 0:
+        return []
+    exact = _exact_default() if exact is None else exact
+    dev = images[0].device
+    dtype = images[0].dtype
+    if dtype not in _DT:
+        raise TypeError("detectinblur_b200 blurs float32 or float16 images, got %s" % dtype)
+    results = []
+    descs = (_lib.Image * n)()
+    keep = []
+    for k, img in enumerate(images):
+        psf_ops._require_cuda(img, "image %d" % k)
+        if img.dim() != 3:
+            raise ValueError("images must be [C, H, W], got %s" % (tuple(img.shape),))
+        if img.dtype != dtype or img.device != dev:
+            raise TypeError("all images of a batch must share dtype and device")
+        if img.stride(2) != 1 or (img.shape[0] > 1 and img.stride(0) < img.stride(1) * img.shape[1]):
+            img = img.contiguous()
+        keep.append(img)
+        C, H, W = (int(s) for s in img.shape)
+        if outs is not None and outs[k] is not None:
+            out = outs[k]
+            if out.dtype != dtype or out.device != dev or out.dim() != 3 or out.stride(2) != 1:
+                raise ValueError("bad destination tensor for image %d" % k)
+        else:
+            out = torch.empty((C, H, W), dtype=dtype, device=dev)
+        results.append(out)
+        d = descs[k]
+        d.src, d.dst = img.data_ptr(), out.data_ptr()
+        d.C, d.H, d.W = C, H, W
+        d.psf_index = int(psf_indices[k])
+        d.src_row_pitch, d.src_chan_pitch = img.stride(1), img.stride(0)
+        d.dst_row_pitch, d.dst_chan_pitch = out.stride(1), out.stride(0)
+        d.pad_mode = pad_mode_for(tapset.side, H, W) if d.psf_index >= 0 else _lib.PAD_REFLECT128
+        epi = 0
+        if noise_sd is not None and noise_sd[k] is not None:
+            nz = noise[k] if noise is not None else None
+            if nz is not None:
+                nz = nz.to(dtype).expand(C, H, W) if nz.shape != out.shape else nz
+                if nz.stride() != out.stride():
+                    raise ValueError("noise tensor %d must have the destination's layout" % k)
+                keep.append(nz)
+                d.noise = nz.data_ptr()
+                epi |= _lib.EPI_NOISE
+            elif philox_seed is not None:
+                epi |= _lib.EPI_NOISE | _lib.EPI_PHILOX
+            d.noise_sd = float(noise_sd[k])
+            if clamp is None or clamp[k]:
+                epi |= _lib.EPI_CLAMP
+        elif clamp is not None and clamp[k]:
+            epi |= _lib.EPI_CLAMP
+        if gamma is not None and gamma[k] is not None:
+            epi |= _lib.EPI_GAMMA
+            d.gamma = float(gamma[k])
+        if mean is not None and mean[k] is not None:
+            epi |= _lib.EPI_NORMALIZE
+            for c in range(min(C, 4)):
+                d.mean[c] = float(mean[k][c])
+                d.std[c] = float(std[k][c])
+        d.epilogue = epi
+    algo = _lib.ALGO_GENERIC if exact else _lib.ALGO_AUTO
+    launches = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        stream = psf_ops._stream_ptr(dev)
+        for lo in range(0, n, _lib.MAX_BATCH):
+            cnt = min(_lib.MAX_BATCH, n - lo)
+            sub = ctypes.cast(ctypes.byref(descs, lo * ctypes.sizeof(_lib.Image)), ctypes.POINTER(_lib.Image))
+            _lib.check(_lib.lib.dib_blur_batch(sub, cnt, ctypes.c_void_p(tapset.buffer.data_ptr()) if tapset is not None else None,
+                                               tapset.n_psfs if tapset is not None else 0,
+                                               tapset.max_taps if tapset is not None else 0,
+                                               tapset.meta if tapset is not None else None, _DT[dtype], algo,
+                                               int(philox_seed or 0), lo, ctypes.byref(launches), stream))
+            _launch_count += launches.value
+    return results
+
+
+def _draw_effects(add_noise, noise_level, add_block, add_jpeg_artifact):
+    """Consume numpy's global RNG exactly as one manual_blur call does (blur_functions.py:72-87): the draws do not
+    depend on pixel data, so they are made up front, image by image, and applied after the batched launch."""
+    d = {"noise_var": None, "block_scale": None, "jpeg_quality": None}
+    if add_noise:
+        d["noise_var"] = np.random.uniform(0.00000001, noise_level)          # :73
+    if add_block:
+        if np.random.uniform(0, 1) > 0.5:                                    # :77
+            d["block_scale"] = np.random.uniform(0.6, 1)                      # :79
+    if add_jpeg_artifact:
+        if np.random.uniform(0, 1) > 0.35:                                   # :85
+            d["jpeg_quality"] = np.random.uniform(20, 90)                     # :86
+    return d
+
+
+def _post_effects(output, draws, jpeg_compressor):
+    """Block and JPEG artefacts stay torch code, exactly as in the reference (blur_functions.py:76-87)."""
+    if draws["block_scale"] is not None:
+        original_shape = output.shape
+        scale_factor = draws["block_scale"]
+        output = torch.nn.functional.interpolate(output.unsqueeze(axis=0), scale_factor=(scale_factor, scale_factor),
+                                                 mode='nearest').squeeze()
+        output = torch.nn.functional.interpolate(output.unsqueeze(axis=0), size=original_shape[1:], mode='nearest').squeeze()
+    if draws["jpeg_quality"] is not None:
+        from . import transforms
+        output = transforms.add_jpeg_artifact_to_image(output, jpeg_compressor, draws["jpeg_quality"])
+    return output
+
+
+def manual_blur(image_GPU, psf_GPU, add_noise=False, noise_level=0.001, add_block=False, add_jpeg_artifact=False,
+                jpeg_compressor=None, exact=None):
+    """blur_functions.py:11-89.  image is CxHxW, psf is kxk (k <= 129: centre 63; larger: centre 127) and normalised."""
+    psf_ops._require_cuda(image_GPU, "image_GPU")
+    psf_ops._require_cuda(psf_GPU, "psf_GPU")
+    if psf_GPU.dim() != 2:
+        raise ValueError("psf must be k x k")
+    pad_mode_for(int(psf_GPU.shape[0]), int(image_GPU.shape[1]), int(image_GPU.shape[2]))   # raises like the reference
+    # the 0-dim PSF element multiplies in the image dtype (torch type promotion), so taps live in that dtype
+    tapset = psf_ops.compact_taps(psf_GPU.to(image_GPU.dtype), normalize=False)
+    draws = _draw_effects(add_noise, noise_level, add_block, add_jpeg_artifact)
+    noise = noise_sd = None
+    if add_noise:
+        noise = [torch.randn(image_GPU.shape, dtype=image_GPU.dtype, device=image_GPU.device)]   # :74 randn_like
+        noise_sd = [math.sqrt(draws["noise_var"])]
+    output = blur_batch([image_GPU], tapset, [0], noise=noise, noise_sd=noise_sd, exact=exact)[0]
+    output = output.squeeze()                                                       # :69
+    return _post_effects(output, draws, jpeg_compressor)
+
+
+def blur_image_list(images_GPU, blur_dicts, psfs_GPU, add_noise=False, noise_level=0.001, add_block=False,
+                    add_jpeg_artifact=False, jpeg_compressor=None, exact=None):
+    """blur_functions.py:92-100: blur, in place, every list entry whose ``blur_dict["blurring"]`` is truthy.
+
+    Each PSF is normalised by its own sum (:98) during tap compaction; entries that are not blurred keep their
+    identity.  Random draws happen image by image in list order, as in the reference.
+    """
+    idx = [k for k, bd in enumerate(blur_dicts) if bd["blurring"]]
+    if not idx:
+        return None
+    # group by (image dtype, PSF side): one compaction + one blur call per group
+    groups = {}
+    for k in idx:
+        psf_ops._require_cuda(images_GPU[k], "images_GPU[%d]" % k)
+        psf_ops._require_cuda(psfs_GPU[k], "psfs_GPU[%d]" % k)
+        key = (images_GPU[k].dtype, int(psfs_GPU[k].shape[0]), psfs_GPU[k].dtype)
+        groups.setdefault(key, []).append(k)
+    draws, noise_t = {}, {}
+    for k in idx:   # reference order: per blurred image, its numpy draws and its randn_like
+        draws[k] = _draw_effects(add_noise, noise_level, add_block, add_jpeg_artifact)
+        if add_noise:
+            noise_t[k] = torch.randn(images_GPU[k].shape, dtype=images_GPU[k].dtype, device=images_GPU[k].device)
+    for (img_dtype, side, psf_dtype), members in groups.items():
+        for k in members:
+            pad_mode_for(side, int(images_GPU[k].shape[1]), int(images_GPU[k].shape[2]))
+        psfs = torch.stack([psfs_GPU[k] for k in members])
+        if psf_dtype == img_dtype:
+            tapset = psf_ops.compact_taps(psfs, normalize=True)
+        else:
+            # the reference multiplies by the 0-dim normalised PSF element cast to the image dtype: normalise in the
+            # PSF dtype, cast, then compact, so tap weights carry exactly that rounding
+            dense = torch.stack([p / p.sum() for p in psfs])
+            tapset = psf_ops.compact_taps(dense.to(img_dtype), normalize=False)
+        noise = [noise_t[k] for k in members] if add_noise else None
+        noise_sd = [math.sqrt(draws[k]["noise_var"]) for k in members] if add_noise else None
+        outs = blur_batch([images_GPU[k] for k in members], tapset, list(range(len(members))), noise=noise,
+                          noise_sd=noise_sd, exact=exact)
+        for k, out in zip(members, outs):
+            images_GPU[k] = _post_effects(out.squeeze(), draws[k], jpeg_compressor)
+    return None

@@ -1,0 +1,102 @@
+// dib_blur_batch: validation, kernel selection and launch planning for the batched blur (include/dib.h).
+//
+// Stands where the reference has blur_image_list's Python loop (models/blur_functions.py:92-100) calling
+// manual_blur (:11-89) once per image: one call here blurs the whole batch with at most two launches (tiled
+// kernel for eligible images, exact-order kernel for the rest).
+#include "dib_common.cuh"
+
+namespace dib {
+int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
+                   int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
+int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
+                 uint64_t seed, uint64_t offset, cudaStream_t st);
+
+static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
+    if (meta_host == nullptr || io_dtype != DIB_F32 || im.psf_index < 0) return false;
+    if (im.pad_mode != DIB_PAD_REFLECT128 || im.H <= 64 || im.W <= 64) return false;
+    const dib_psf_meta& m = meta_host[im.psf_index];
+    if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return false;
+    if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) return false;
+    return true;
+}
+}  // namespace dib
+
+extern "C" int dib_blur_batch(const dib_image* images, int n_images, const void* tapset, int n_psfs, int max_taps,
+                              const dib_psf_meta* meta_host, int io_dtype, int algo, uint64_t philox_seed,
+                              uint64_t philox_offset, int* launches, void* stream) {
+    using namespace dib;
+    if (launches) *launches = 0;
+    DIB_CHECK_ARG(images != nullptr, "dib_blur_batch: images is NULL");
+    DIB_CHECK_ARG(n_images >= 0 && n_images <= DIB_MAX_BATCH, "dib_blur_batch: n_images %d outside [0, %d]", n_images, DIB_MAX_BATCH);
+    DIB_CHECK_ARG(io_dtype == DIB_F32 || io_dtype == DIB_F16, "dib_blur_batch: io_dtype must be DIB_F32 or DIB_F16");
+    DIB_CHECK_ARG(algo == DIB_ALGO_AUTO || algo == DIB_ALGO_GENERIC || algo == DIB_ALGO_TILED, "dib_blur_batch: unknown algo %d", algo);
+    if (n_images == 0) return DIB_OK;
+    bool any_psf = false;
+    for (int k = 0; k < n_images; ++k) {
+        const dib_image& im = images[k];
+        DIB_CHECK_ARG(im.src != nullptr && im.dst != nullptr, "dib_blur_batch: image %d has a NULL buffer", k);
+        DIB_CHECK_ARG(im.src != im.dst, "dib_blur_batch: image %d: dst must not alias src", k);
+        DIB_CHECK_ARG(im.C >= 1 && im.H >= 1 && im.W >= 1, "dib_blur_batch: image %d has an empty shape %dx%dx%d", k, im.C, im.H, im.W);
+        DIB_CHECK_ARG(im.src_row_pitch >= im.W && im.dst_row_pitch >= im.W, "dib_blur_batch: image %d: row pitch smaller than W", k);
+        DIB_CHECK_ARG(im.psf_index < n_psfs, "dib_blur_batch: image %d: psf_index %d >= n_psfs %d", k, im.psf_index, n_psfs);
+        DIB_CHECK_ARG(im.pad_mode >= DIB_PAD_REFLECT128 && im.pad_mode <= DIB_PAD_REPLICATE256, "dib_blur_batch: image %d: bad pad_mode", k);
+        if (im.psf_index >= 0 && im.pad_mode == DIB_PAD_REFLECT128 && (im.H <= 64 || im.W <= 64)) {
+            // the reference raises here: torch reflect padding needs pad (64) < dim  (blur_functions.py:57-59)
+            set_error("dib_blur_batch: image %d (%dx%d): reflect padding of 64 needs every side > 64", k, im.H, im.W);
+            return DIB_ERR_UNSUPPORTED;
+        }
+        if ((im.epilogue & DIB_EPI_NORMALIZE) && im.C > 4) {
+            set_error("dib_blur_batch: image %d: fused normalize supports at most 4 channels", k);
+            return DIB_ERR_UNSUPPORTED;
+        }
+        any_psf |= im.psf_index >= 0;
+    }
+    DIB_CHECK_ARG(!any_psf || (tapset != nullptr && n_psfs > 0 && max_taps > 0), "dib_blur_batch: tap set missing");
+    const dib_tapset_layout L = tapset_layout(n_psfs > 0 ? n_psfs : 1, max_taps > 0 ? max_taps : 1);
+    const uint8_t* base = static_cast<const uint8_t*>(tapset);
+    const dib_psf_meta* meta_dev = reinterpret_cast<const dib_psf_meta*>(base + L.meta_offset);
+    const dib_tap* taps = reinterpret_cast<const dib_tap*>(base + L.taps_offset);
+    const uint8_t* prog = base + L.prog_offset;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    // split the batch: tiled kernel where eligible (heaviest PSFs first), exact-order kernel for the rest
+    int order[DIB_MAX_BATCH];
+    int n_sel = 0;
+    uint32_t tiled_mask = 0;
+    if (algo != DIB_ALGO_GENERIC) {
+        for (int k = 0; k < n_images; ++k) {
+            if (tiled_eligible(images[k], meta_host, io_dtype)) {
+                order[n_sel++] = k;
+                tiled_mask |= 1u << k;
+            } else if (algo == DIB_ALGO_TILED) {
+                set_error("dib_blur_batch: image %d is not eligible for the tiled kernel (fp32, reflect mode, sides > 64, "
+                          "PSF with a tiled program and host meta required)", k);
+                return DIB_ERR_UNSUPPORTED;
+            }
+        }
+        // insertion sort by tap count, descending (stable): long tiles are scheduled first
+        for (int a = 1; a < n_sel; ++a) {
+            const int v = order[a];
+            const int cv = meta_host[images[v].psf_index].count;
+            int b = a - 1;
+            while (b >= 0 && meta_host[images[order[b]].psf_index].count < cv) {
+                order[b + 1] = order[b];
+                --b;
+            }
+            order[b + 1] = v;
+        }
+    }
+    int nl = 0;
+    if (n_sel > 0) {
+        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, philox_seed, philox_offset, st);
+        if (rc != DIB_OK) return rc;
+        ++nl;
+    }
+    if (n_sel < n_images) {
+        const int rc = launch_generic(images, n_images, taps, meta_dev, max_taps, io_dtype, tiled_mask, philox_seed, philox_offset, st);
+        if (rc != DIB_OK) return rc;
+        ++nl;
+    }
+    if (launches) *launches = nl;
+    return DIB_OK;
+}

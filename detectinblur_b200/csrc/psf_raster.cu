@@ -1,0 +1,241 @@
+// GPU PSF rasterisation: seeded trajectories -> dense PSFs, bit-identical to the reference's fp64 Python loops.
+//
+// Replaces, per PSF (about 45 ms of Python on the host):
+//   PSF.fit           motion_blur/generate_PSF.py:31-77   exposure-fraction time slicing (:47-56), 4-corner bilinear
+//                                                          splat (:59-75), division by iters (:77)
+//   PSF.centerPSF     motion_blur/generate_PSF.py:106-123 np.sum, weighted centroid, int() truncation, np.roll
+//   crop [64:192]     transforms.py:334-335
+//   astype(float16)   dataset_utils/generate_PSFs.py:60
+// The trajectory itself (motion_blur/generate_trajectory.py:38-98) is a sequential random walk on numpy's MT19937
+// stream and stays on the host: its samples are this kernel's input.
+//
+// Bit-exactness: a PSF cell's value is a chain of fp64 additions in ascending sample order.  The kernel gives
+// every cell of the trajectory's bounding box to one thread, which walks the samples in order and adds exactly
+// the contributions the Python loop adds (same expression, no FMA contraction), so parallelism is across cells
+// only.  np.sum's pairwise tree (blocks of 128 with 8 strided partial sums, then a balanced binary tree) and the
+// row-major centroid accumulation are reproduced as well, because the centring offset is an int() truncation.
+#include "dib_common.cuh"
+
+namespace dib {
+
+constexpr int kRasterThreads = 512;
+
+__device__ __forceinline__ double tri(double v) { return fmax(0.0, __dsub_rn(1.0, fabs(v))); }
+
+// generate_PSF.py:47-56 with a single fraction (prevT = 0)
+__device__ __forceinline__ double time_weight(int t, double fraction, int iters) {
+    const double fi = __dmul_rn(fraction, (double)iters);
+    const double prev = 0.0;
+    if (fi >= (double)t && prev < (double)(t - 1)) return 1.0;
+    if (fi >= (double)(t - 1) && prev < (double)(t - 1)) return __dsub_rn(fi, (double)(t - 1));
+    if (fi >= (double)t && prev < (double)t) return __dsub_rn((double)t, prev);
+    if (fi >= (double)(t - 1) && prev < (double)t) return __dmul_rn(__dsub_rn(fraction, 0.0), (double)iters);
+    return 0.0;
+}
+
+template <typename T>
+__device__ __forceinline__ T cast_out(double v);
+template <>
+__device__ __forceinline__ double cast_out<double>(double v) { return v; }
+template <>
+__device__ __forceinline__ float cast_out<float>(double v) { return (float)v; }
+template <>
+__device__ __forceinline__ __half cast_out<__half>(double v) { return __double2half(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kRasterThreads)
+rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__ fractions, int iters, int canvas, int center,
+                     int out_side, T* __restrict__ out, int32_t* __restrict__ offsets, double* __restrict__ scratch) {
+    extern __shared__ __align__(16) uint8_t raster_smem[];
+    double* s_re = reinterpret_cast<double*>(raster_smem);
+    double* s_im = s_re + iters;
+    double* s_w = s_im + iters;
+    short2* s_m = reinterpret_cast<short2*>(s_w + iters);   // (m1 = row, m2 = col) per sample
+    __shared__ int s_red[4][kRasterThreads / 32];
+    __shared__ int s_box[4];
+    __shared__ int s_tlast;
+    __shared__ double s_tree[512];
+    __shared__ int s_off[2];
+
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double fraction = fractions[n];
+    const double* tr = traj + (size_t)n * iters * 2;
+    double* canvas_buf = scratch + (size_t)n * canvas * canvas;
+    const int cells = canvas * canvas;
+
+    // 0. clear the scratch canvas
+    for (int i = tid; i < cells; i += kRasterThreads) canvas_buf[i] = 0.0;
+
+    // 1. samples, base cells and time weights
+    int ymin = 1 << 20, ymaxn = 1 << 20, xmin = 1 << 20, xmaxn = 1 << 20, tlast = 0;
+    for (int t = tid; t < iters; t += kRasterThreads) {
+        const double re = tr[2 * t], im = tr[2 * t + 1];
+        s_re[t] = re;
+        s_im[t] = im;
+        const double w = time_weight(t, fraction, iters);
+        s_w[t] = w;
+        // m = min(canvas - 1, max(1, floor(v)))   (generate_PSF.py:59-62)
+        const int m2 = (int)fmin((double)(canvas - 1), fmax(1.0, floor(re)));
+        const int m1 = (int)fmin((double)(canvas - 1), fmax(1.0, floor(im)));
+        s_m[t] = make_short2((short)m1, (short)m2);
+        if (w != 0.0) {
+            ymin = min(ymin, m1);
+            ymaxn = min(ymaxn, -(m1 + 1));
+            xmin = min(xmin, m2);
+            xmaxn = min(xmaxn, -(m2 + 1));
+            tlast = max(tlast, t);
+        }
+    }
+    int v4[4] = {ymin, ymaxn, xmin, xmaxn};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v4[k] = min(v4[k], __shfl_xor_sync(0xffffffffu, v4[k], o));
+        if (lane == 0) s_red[k][warp] = v4[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tlast = max(tlast, __shfl_xor_sync(0xffffffffu, tlast, o));
+    __syncthreads();
+    if (tid == 0) s_tlast = 0;
+    __syncthreads();
+    if (lane == 0) atomicMax(&s_tlast, tlast);
+    if (tid < 4) {
+        int m = s_red[tid][0];
+        for (int k = 1; k < kRasterThreads / 32; ++k) m = min(m, s_red[tid][k]);
+        s_box[tid] = m;
+    }
+    __syncthreads();
+    const int y0 = s_box[0], y1 = min(-s_box[1], canvas - 1), x0 = s_box[2], x1 = min(-s_box[3], canvas - 1);
+    const int t_last = s_tlast;
+    const bool empty = (y0 > y1) || (x0 > x1);
+
+    // 2. one thread per cell of the bounding box; contributions added in ascending sample order
+    if (!empty) {
+        const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+        for (int cidx = tid; cidx < bw * bh; cidx += kRasterThreads) {
+            const int cy = y0 + cidx / bw, cx = x0 + cidx % bw;
+            double acc = 0.0;
+            for (int t = 0; t <= t_last; ++t) {
+                const short2 m = s_m[t];
+                const int dy = cy - m.x, dx = cx - m.y;
+                if ((unsigned)dy <= 1u && (unsigned)dx <= 1u) {
+                    // t_proportion * triangle_fun_prod(re - col, im - row)   (generate_PSF.py:64-75)
+                    const double v = __dmul_rn(s_w[t], __dmul_rn(tri(__dsub_rn(s_re[t], (double)cx)), tri(__dsub_rn(s_im[t], (double)cy))));
+                    acc = __dadd_rn(acc, v);
+                }
+            }
+            canvas_buf[cy * canvas + cx] = __ddiv_rn(acc, (double)iters);   // PSF / iters (:77)
+        }
+    }
+    __syncthreads();
+
+    int ox = 0, oy = 0;
+    if (center && !empty) {
+        // 3. totalSum = np.sum(psf): numpy's pairwise summation over the flattened canvas.  Blocks of 128 elements use
+        //    8 strided partial sums combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); blocks combine in a balanced tree.
+        const int nblocks = cells / 128;       // canvas is a power of two >= 16 (checked on the host)
+        double total = 0.0;
+        for (int base = 0; base < nblocks; base += 512) {
+            const int nb = min(512, nblocks - base);
+            for (int b = tid; b < nb; b += kRasterThreads) {
+                const double* a = canvas_buf + (size_t)(base + b) * 128;
+                double r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = a[j];
+                for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+                }
+                s_tree[b] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                      __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+            }
+            __syncthreads();
+            for (int stride = 1; stride < nb; stride <<= 1) {
+                for (int b = tid * 2 * stride; b + stride < nb; b += kRasterThreads * 2 * stride)
+                    s_tree[b] = __dadd_rn(s_tree[b], s_tree[b + stride]);
+                __syncthreads();
+            }
+            // canvases above 256 would need the partial results of successive 512-block groups combined pairwise too;
+            // the host restricts canvas to <= 256 so there is exactly one group
+            total = s_tree[0];
+            __syncthreads();
+        }
+        // 4. weighted centroid over cells with psf > 0, row-major, sequential fp64 (generate_PSF.py:110-117)
+        if (warp == 0) {
+            double ax = 0.0, ay = 0.0;
+            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1, nbox = bw * bh;
+            for (int base = 0; base < nbox; base += 32) {
+                const int cidx = base + lane;
+                double v = 0.0;
+                int cy = 0, cx = 0;
+                if (cidx < nbox) {
+                    cy = y0 + cidx / bw;
+                    cx = x0 + cidx % bw;
+                    v = canvas_buf[cy * canvas + cx];
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, v > 0.0);
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const double vv = __shfl_sync(0xffffffffu, v, src);
+                    const int yy = __shfl_sync(0xffffffffu, cy, src), xx = __shfl_sync(0xffffffffu, cx, src);
+                    const double weight = __ddiv_rn(vv, total);
+                    ax = __dadd_rn(ax, __dmul_rn((double)xx, weight));
+                    ay = __dadd_rn(ay, __dmul_rn((double)yy, weight));
+                }
+            }
+            if (lane == 0) {
+                s_off[0] = (int)__dsub_rn(ax, (double)canvas / 2.0);   // int(): truncation toward zero (:119-120)
+                s_off[1] = (int)__dsub_rn(ay, (double)canvas / 2.0);
+            }
+        }
+        __syncthreads();
+        ox = s_off[0];
+        oy = s_off[1];
+    }
+    if (tid == 0 && offsets != nullptr) {
+        offsets[2 * n] = ox;
+        offsets[2 * n + 1] = oy;
+    }
+
+    // 5. np.roll by (-offsetX, -offsetY), central crop, cast   (generate_PSF.py:122-123, transforms.py:334-335)
+    const int crop0 = (canvas - out_side) / 2;
+    T* o = out + (size_t)n * out_side * out_side;
+    for (int i = tid; i < out_side * out_side; i += kRasterThreads) {
+        const int yy = crop0 + i / out_side, xx = crop0 + i % out_side;
+        const int sy = ((yy + oy) % canvas + canvas) % canvas, sx = ((xx + ox) % canvas + canvas) % canvas;
+        o[i] = cast_out<T>(canvas_buf[sy * canvas + sx]);
+    }
+}
+
+}  // namespace dib
+
+extern "C" int dib_rasterize_psf(const double* traj, const double* fractions, int n, int iters, int canvas, int center,
+                                 int out_side, void* out, int out_dtype, int32_t* offsets, double* scratch, void* stream) {
+    using namespace dib;
+    DIB_CHECK_ARG(traj != nullptr && fractions != nullptr && out != nullptr && scratch != nullptr, "dib_rasterize_psf: null buffer");
+    DIB_CHECK_ARG(n > 0, "dib_rasterize_psf: n must be > 0");
+    DIB_CHECK_ARG(iters >= 2 && iters <= 4096, "dib_rasterize_psf: iters %d outside [2, 4096]", iters);
+    DIB_CHECK_ARG(canvas >= 16 && canvas <= 256 && (canvas & (canvas - 1)) == 0,
+                  "dib_rasterize_psf: canvas must be a power of two in [16, 256] (got %d)", canvas);
+    DIB_CHECK_ARG(out_side > 0 && out_side <= canvas && ((canvas - out_side) % 2) == 0,
+                  "dib_rasterize_psf: out_side %d must be <= canvas with an even margin", out_side);
+    DIB_CHECK_ARG(out_dtype == DIB_F64 || out_dtype == DIB_F32 || out_dtype == DIB_F16, "dib_rasterize_psf: bad out_dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)iters * (3 * sizeof(double) + sizeof(short2));
+    if (out_dtype == DIB_F64) {
+        DIB_CUDA(cudaFuncSetAttribute(rasterize_psf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rasterize_psf_kernel<double><<<n, kRasterThreads, smem, st>>>(traj, fractions, iters, canvas, center, out_side,
+                                                                       static_cast<double*>(out), offsets, scratch);
+    } else if (out_dtype == DIB_F32) {
+        DIB_CUDA(cudaFuncSetAttribute(rasterize_psf_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rasterize_psf_kernel<float><<<n, kRasterThreads, smem, st>>>(traj, fractions, iters, canvas, center, out_side,
+                                                                      static_cast<float*>(out), offsets, scratch);
+    } else {
+        DIB_CUDA(cudaFuncSetAttribute(rasterize_psf_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rasterize_psf_kernel<__half><<<n, kRasterThreads, smem, st>>>(traj, fractions, iters, canvas, center, out_side,
+                                                                       static_cast<__half*>(out), offsets, scratch);
+    }
+    DIB_CUDA(cudaGetLastError());
+    return DIB_OK;
+}

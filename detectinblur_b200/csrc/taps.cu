@@ -1,0 +1,328 @@
+// Tap compaction: dense PSF batch -> per-PSF normalised (y, x, w) lists in the reference's accumulation order,
+// extents / PCA moments, and the column-group program the tiled blur kernel executes.
+//
+// Replaces (per PSF, on the host thread, with device->host syncs) in the reference:
+//   psf_GPU = psf_GPU / psf_GPU.sum()                       models/blur_functions.py:98
+//   non_zero_points = psf_GPU.nonzero(as_tuple=False)       models/blur_functions.py:63
+//   non_zero_points[i, 0] - 63, psf_GPU[y, x] per tap       models/blur_functions.py:67   (2 syncs per tap)
+//   min/max of the nonzero coordinates                      utils.py:372-380 (expand_targets)
+//   first/second moments of the support                     transforms.py:366-376 (PSF PCA)
+// One CTA per PSF, one launch per batch.
+#include "dib_common.cuh"
+
+namespace dib {
+
+constexpr int kCompactThreads = 256;
+
+template <typename T>
+struct PsfNum;
+template <>
+struct PsfNum<float> {
+    // fp32 PSF: torch sums in fp32 and divides with IEEE division.  The sum is accumulated in fp64 here and
+    // rounded once; for PSFs on the fp16 grid summing below 1 (every stored / generated PSF) every fp32
+    // partial sum is exact, so this equals torch's result whatever its reduction order.
+    __device__ static float load(const float* p, int64_t i) { return p[i]; }
+    __device__ static float round_sum(double s) { return (float)s; }
+    __device__ static float normalized(float v, float s) { return __fdiv_rn(v, s); }
+};
+template <>
+struct PsfNum<__half> {
+    // half PSF: torch's CUDA sum accumulates in fp32 and rounds to half; half / half divides in fp32 and rounds.
+    __device__ static float load(const __half* p, int64_t i) { return __half2float(p[i]); }
+    __device__ static float round_sum(double s) { return __half2float(__float2half_rn((float)s)); }
+    __device__ static float normalized(float v, float s) { return __half2float(__float2half_rn(__fdiv_rn(v, s))); }
+};
+
+__device__ inline double block_sum_double(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[w];  // fixed order: deterministic
+    return t;
+}
+
+__device__ inline long long block_sum_ll(long long v, long long* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[w];
+    return t;
+}
+
+__device__ inline int block_min_int(int v, int* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    int t = sh[0];
+#pragma unroll
+    for (int w = 1; w < kCompactThreads / 32; ++w) t = min(t, sh[w]);
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
+                    dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog) {
+    __shared__ double sh_d[kCompactThreads / 32];
+    __shared__ long long sh_ll[kCompactThreads / 32];
+    __shared__ int sh_i[kCompactThreads / 32];
+    __shared__ int sh_warp_count[kCompactThreads / 32];
+    __shared__ int sh_running;
+    __shared__ unsigned sh_occ[32 * 4];
+    __shared__ ChunkRec sh_chunks[kProgMaxChunks];
+    __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
+    __shared__ int sh_nchunks, sh_total_steps;
+
+    const int n = blockIdx.x;
+    const T* psf = psfs + (int64_t)n * psf_stride;
+    const int cells = side * side;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // 1. psf.sum() (blur_functions.py:98)
+    double part = 0.0;
+    for (int i = tid; i < cells; i += kCompactThreads) part += (double)PsfNum<T>::load(psf, i);
+    const double total = block_sum_double(part, sh_d);
+    const float s = PsfNum<T>::round_sum(total);
+
+    // 2. ordered compaction of the normalised PSF (row-major nonzero order, blur_functions.py:63)
+    if (tid == 0) sh_running = 0;
+    int ymin = 1 << 20, ymax_neg = 1 << 20, xmin = 1 << 20, xmax_neg = 1 << 20;  // max kept as min of negatives
+    long long sy = 0, sx = 0, syy = 0, sxx = 0, sxy = 0, support = 0;
+    __syncthreads();
+    for (int base = 0; base < cells; base += kCompactThreads) {
+        const int i = base + tid;
+        float v = 0.0f, w = 0.0f;
+        if (i < cells) {
+            v = PsfNum<T>::load(psf, i);
+            w = normalize ? PsfNum<T>::normalized(v, s) : v;
+        }
+        const bool nz = (w != 0.0f);
+        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) sh_warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        int offset = sh_running;
+        for (int k = 0; k < warp; ++k) offset += sh_warp_count[k];
+        const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
+        const int y = i / side, x = i - y * side;
+        if (nz) {
+            if (pos < max_taps) {
+                dib_tap t;
+                t.y = (int16_t)y;
+                t.x = (int16_t)x;
+                t.w = w;
+                taps[(int64_t)n * max_taps + pos] = t;
+            }
+            ymin = min(ymin, y);
+            ymax_neg = min(ymax_neg, -y);
+            xmin = min(xmin, x);
+            xmax_neg = min(xmax_neg, -x);
+        }
+        if (i < cells && v > 0.0f) {  // support of the PCA: psf > 0 (transforms.py:366)
+            support += 1;
+            sy += y;
+            sx += x;
+            syy += (long long)y * y;
+            sxx += (long long)x * x;
+            sxy += (long long)y * x;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0;
+            for (int k = 0; k < kCompactThreads / 32; ++k) c += sh_warp_count[k];
+            sh_running += c;
+        }
+        __syncthreads();
+    }
+    const int count = sh_running;
+    ymin = block_min_int(ymin, sh_i);
+    const int ymax = -block_min_int(ymax_neg, sh_i);
+    xmin = block_min_int(xmin, sh_i);
+    const int xmax = -block_min_int(xmax_neg, sh_i);
+    support = block_sum_ll(support, sh_ll);
+    sy = block_sum_ll(sy, sh_ll);
+    sx = block_sum_ll(sx, sh_ll);
+    syy = block_sum_ll(syy, sh_ll);
+    sxx = block_sum_ll(sxx, sh_ll);
+    sxy = block_sum_ll(sxy, sh_ll);
+
+    // 3. chunked column-group program for the tiled kernel (layout in dib_common.cuh, consumer blur_tiled.cu)
+    const int centre = side > 129 ? 127 : 63;
+    int flags = 0;
+    if (count > max_taps) flags |= DIB_META_TRUNCATED;
+    uint8_t* my_prog = prog + (size_t)n * kProgBytes;
+    ChunkRec* out_chunks = reinterpret_cast<ChunkRec*>(my_prog);
+    // taps at dy or dx >= 64 (PSF row/col >= 127) hit torch.roll's wrap-around at output row/col 0; those PSFs
+    // (never produced by the centred generator) stay on the generic kernel, which restates the wrap exactly.
+    const bool want_prog = side <= 129 && count > 0 && ymax <= 126 && xmax <= 126;
+    if (tid == 0) {
+        sh_nchunks = 0;
+        sh_total_steps = 0;
+    }
+    __syncthreads();
+    if (want_prog) {
+        const int ngroups = (xmax - xmin + kGroupW) / kGroupW;   // <= 32 for side <= 129
+        // 3a. per group: bitmask of the PSF rows holding a tap in the group's columns (rows 0..127 -> 4 words)
+        for (int k = tid; k < ngroups * 4; k += kCompactThreads) sh_occ[k] = 0u;
+        __syncthreads();
+        for (int k = tid; k < ngroups * (ymax - ymin + 1); k += kCompactThreads) {
+            const int g = k / (ymax - ymin + 1), y = ymin + k % (ymax - ymin + 1);
+            bool any = false;
+            for (int e = 0; e < kGroupW; ++e) {
+                const int x = xmin + g * kGroupW + e;
+                if (x < side) {
+                    const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                    const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                    any |= (w != 0.0f);
+                }
+            }
+            if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
+        }
+        __syncthreads();
+        // 3b. one thread packs segments into chunks (a few dozen iterations of bit scans)
+        if (tid == 0) {
+            int nchunks = 0, data_off = (int)kProgHeaderBytes, total_steps = 0;
+            bool ok = true;
+            for (int g0 = 0; g0 < ngroups && ok; g0 += kChunkGroups) {
+                const int g1 = min(g0 + kChunkGroups, ngroups);
+                int cursor = ymin;
+                while (ok) {
+                    // first occupied row >= cursor in this band of groups
+                    int y0 = -1;
+                    for (int y = cursor; y <= ymax && y0 < 0; ++y)
+                        for (int g = g0; g < g1; ++g)
+                            if ((sh_occ[g * 4 + (y >> 5)] >> (y & 31)) & 1u) { y0 = y; break; }
+                    if (y0 < 0) break;
+                    const int y1 = min(y0 + kChunkHaloRows, ymax);
+                    if (nchunks >= kProgMaxChunks) { ok = false; break; }
+                    ChunkRec c;
+                    SegRec segs[kChunkGroups];
+                    int nseg = 0, wsteps = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
+                    for (int g = g0; g < g1; ++g) {
+                        int f = -1, l = -1;
+                        for (int y = y0; y <= y1; ++y)
+                            if ((sh_occ[g * 4 + (y >> 5)] >> (y & 31)) & 1u) { if (f < 0) f = y; l = y; }
+                        if (f < 0) continue;
+                        SegRec sg;
+                        sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
+                        sg.dy0 = (int16_t)(f - centre);
+                        sg.nsteps = (int16_t)(l - f + 1);
+                        sg.woff = (int16_t)wsteps;
+                        wsteps += l - f + 1;
+                        lo = min(lo, f - centre);
+                        hi = max(hi, l - centre);
+                        xlo = min(xlo, (int)sg.dx0);
+                        xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
+                        segs[nseg++] = sg;
+                    }
+                    const int bytes = kChunkSegBytes + 16 * wsteps;
+                    if (data_off + bytes > (int)kProgBytes) { ok = false; break; }
+                    c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
+                    c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
+                    c.nseg = (int16_t)nseg; c.wsteps = (int16_t)wsteps;
+                    c.data_off = data_off;
+                    out_chunks[nchunks] = c;
+                    sh_chunks[nchunks] = c;
+                    SegRec* dst = reinterpret_cast<SegRec*>(my_prog + data_off);
+                    for (int k = 0; k < kChunkGroups; ++k) {
+                        SegRec z; z.dx0 = 0; z.dy0 = 0; z.nsteps = 0; z.woff = 0;
+                        dst[k] = k < nseg ? segs[k] : z;
+                        sh_segs[nchunks * kChunkGroups + k] = k < nseg ? segs[k] : z;
+                    }
+                    data_off += bytes;
+                    total_steps += wsteps;
+                    ++nchunks;
+                    cursor = y1 + 1;
+                }
+            }
+            sh_nchunks = ok ? nchunks : -1;
+            sh_total_steps = total_steps;
+        }
+        __syncthreads();
+        // 3c. all threads fill the weight vectors
+        const int nchunks = sh_nchunks;
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const ChunkRec c = sh_chunks[ci];
+            float* wout = reinterpret_cast<float*>(my_prog + c.data_off + kChunkSegBytes);
+            for (int sgi = 0; sgi < c.nseg; ++sgi) {
+                const SegRec sg = sh_segs[ci * kChunkGroups + sgi];
+                for (int k = tid; k < sg.nsteps * kGroupW; k += kCompactThreads) {
+                    const int step = k / kGroupW, e = k % kGroupW;
+                    const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
+                    float w = 0.0f;
+                    if (x < side) {
+                        const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                        w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                    }
+                    wout[(sg.woff + step) * kGroupW + e] = w;
+                }
+            }
+        }
+    }
+    int nchunks_final = want_prog ? sh_nchunks : -1;
+    if (nchunks_final <= 0) {
+        flags |= DIB_META_NO_PROGRAM;
+        nchunks_final = 0;
+    }
+
+    if (tid == 0) {
+        dib_psf_meta m;
+        m.count = count;
+        m.ymin = (int16_t)(count ? ymin : 0);
+        m.ymax = (int16_t)(count ? ymax : 0);
+        m.xmin = (int16_t)(count ? xmin : 0);
+        m.xmax = (int16_t)(count ? xmax : 0);
+        m.sum = s;
+        m.support = (int32_t)support;
+        m.prog_chunks = nchunks_final;
+        m.prog_steps = nchunks_final ? sh_total_steps : 0;
+        m.flags = flags;
+        m.sy = (double)sy;
+        m.sx = (double)sx;
+        m.syy = (double)syy;
+        m.sxx = (double)sxx;
+        m.sxy = (double)sxy;
+        meta[n] = m;
+    }
+}
+
+}  // namespace dib
+
+extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int side, int64_t psf_stride, int normalize,
+                                void* tapset, int max_taps, void* stream) {
+    using namespace dib;
+    DIB_CHECK_ARG(psfs != nullptr && tapset != nullptr, "dib_compact_taps: null buffer");
+    DIB_CHECK_ARG(n_psfs > 0, "dib_compact_taps: n_psfs must be > 0 (got %d)", n_psfs);
+    DIB_CHECK_ARG(side >= 1 && side <= 512, "dib_compact_taps: PSF side %d outside [1, 512]", side);
+    DIB_CHECK_ARG(psf_stride >= (int64_t)side * side, "dib_compact_taps: psf_stride %lld smaller than one PSF",
+                  (long long)psf_stride);
+    DIB_CHECK_ARG(max_taps > 0, "dib_compact_taps: max_taps must be > 0");
+    DIB_CHECK_ARG(psf_dtype == DIB_F32 || psf_dtype == DIB_F16, "dib_compact_taps: PSF dtype must be DIB_F32 or DIB_F16");
+    const dib_tapset_layout L = tapset_layout(n_psfs, max_taps);
+    uint8_t* base = static_cast<uint8_t*>(tapset);
+    dib_psf_meta* meta = reinterpret_cast<dib_psf_meta*>(base + L.meta_offset);
+    dib_tap* taps = reinterpret_cast<dib_tap*>(base + L.taps_offset);
+    uint8_t* prog = base + L.prog_offset;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (psf_dtype == DIB_F32) {
+        compact_taps_kernel<float><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const float*>(psfs), side, psf_stride,
+                                                                       normalize, meta, taps, max_taps, prog);
+    } else {
+        compact_taps_kernel<__half><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const __half*>(psfs), side, psf_stride,
+                                                                        normalize, meta, taps, max_taps, prog);
+    }
+    DIB_CUDA(cudaGetLastError());
+    return DIB_OK;
+}

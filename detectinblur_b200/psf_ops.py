@@ -1,0 +1,150 @@
+"""Device-side PSF operations over libdib.so: tap compaction, PSF rasterisation, PSF-derived metadata, checksums.
+
+Reference code these stand in for:
+  TapSet / compact_taps   psf/psf.sum() + psf.nonzero() + per-tap index reads   models/blur_functions.py:63-67,98
+  tap_extents             expand_targets' min/max of the nonzero coordinates     utils.py:372-380
+  psf_pca                 PCA of the PSF support (theta, lambda scale factors)   transforms.py:366-385
+  rasterize_psfs          PSF.fit + centerPSF + crop + float16 cast              motion_blur/generate_PSF.py:31-123,
+                                                                                 transforms.py:334-335
+  checksum                per-shard result fingerprint (all-gathered like utils.all_gather, utils.py:536-576)
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_TO_DIB = {torch.float32: _lib.DIB_F32, torch.float16: _lib.DIB_F16, torch.float64: _lib.DIB_F64}
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("detectinblur_b200: %s must be a CUDA tensor (there is no CPU path)" % what)
+
+
+class TapSet(object):
+    """Compacted, normalised taps of a batch of PSFs (device buffer) plus a host copy of the per-PSF summary."""
+
+    def __init__(self, buffer, layout, n_psfs, max_taps, side, meta):
+        self.buffer = buffer            # uint8 CUDA tensor, layout in include/dib.h
+        self.layout = layout
+        self.n_psfs = n_psfs
+        self.max_taps = max_taps
+        self.side = side
+        self.meta = meta                # ctypes array of PsfMeta (host)
+
+    @property
+    def counts(self):
+        return [m.count for m in self.meta]
+
+    def taps(self, index):
+        """(ys, xs, weights) of PSF ``index`` as numpy arrays, in accumulation order (copies device -> host)."""
+        n = min(self.meta[index].count, self.max_taps)
+        off = self.layout.taps_offset + index * self.max_taps * 8
+        raw = self.buffer[off:off + n * 8].cpu().numpy().tobytes()
+        rec = np.frombuffer(raw, dtype=np.dtype([("y", "<i2"), ("x", "<i2"), ("w", "<f4")]))
+        return rec["y"].astype(np.int32), rec["x"].astype(np.int32), rec["w"].copy()
+
+    def tap_extents(self, index, centre=63):
+        """(left, top, right, bottom) tap offsets relative to the centre -- utils.py:375-379."""
+        m = self.meta[index]
+        return m.xmin - centre, m.ymin - centre, m.xmax - centre, m.ymax - centre
+
+    def psf_pca(self, index):
+        """(theta_rad, scale_factor_lambda1, scale_factor_lambda2) from the support moments -- transforms.py:366-385."""
+        m = self.meta[index]
+        n = float(m.support)
+        mean_y, mean_x = m.sy / n, m.sx / n
+        var_y = m.syy / n - mean_y * mean_y
+        var_x = m.sxx / n - mean_x * mean_x
+        cov = m.sxy / n - mean_y * mean_x
+        root = math.sqrt(math.pow((var_x - var_y) / 2, 2) + math.pow(cov, 2))
+        lam1 = (var_x + var_y) / 2 + root
+        lam2 = max((var_x + var_y) / 2 - root, 0.0)
+
+        def sigmoid(v):
+            return 1 / (1 + math.exp(-v))
+
+        s1 = 1 - (sigmoid(math.sqrt(lam1) / 10) - 0.5) * 0.6
+        s2 = 1 - (sigmoid(math.sqrt(lam2) / 10) - 0.5) * 0.6
+        theta = -math.atan2(lam1 - var_x, -cov)
+        return theta, s1, s2
+
+
+def compact_taps(psfs, normalize, max_taps=1024):
+    """Compact a batch of dense PSFs ([n, k, k] or [k, k] CUDA tensor, float32 / float16) into a TapSet.
+
+    One launch for the batch, then one small device->host copy of the per-PSF summaries (counts, extents,
+    program sizes) that the blur launcher plans with.
+    """
+    _require_cuda(psfs, "psfs")
+    if psfs.dim() == 2:
+        psfs = psfs.unsqueeze(0)
+    if psfs.dim() != 3 or psfs.shape[1] != psfs.shape[2]:
+        raise ValueError("psfs must be [n, k, k], got %s" % (tuple(psfs.shape),))
+    if psfs.dtype not in (torch.float32, torch.float16):
+        raise TypeError("PSF dtype must be float32 or float16, got %s" % psfs.dtype)
+    psfs = psfs.contiguous()
+    n, side = int(psfs.shape[0]), int(psfs.shape[1])
+    lay = _lib.tapset_layout(n, max_taps)
+    buf = torch.empty(lay.total_bytes, dtype=torch.uint8, device=psfs.device)
+    with torch.cuda.device(psfs.device):
+        _lib.check(_lib.lib.dib_compact_taps(ctypes.c_void_p(psfs.data_ptr()), _TORCH_TO_DIB[psfs.dtype], n, side,
+                                             side * side, 1 if normalize else 0, ctypes.c_void_p(buf.data_ptr()),
+                                             int(max_taps), _stream_ptr(psfs.device)))
+        meta_bytes = buf[lay.meta_offset:lay.meta_offset + n * ctypes.sizeof(_lib.PsfMeta)].cpu().numpy().tobytes()
+    meta = (_lib.PsfMeta * n).from_buffer_copy(meta_bytes)
+    for k in range(n):
+        if meta[k].flags & _lib.META_TRUNCATED:
+            raise _lib.DibError(_lib.ERR_CAPACITY, "PSF %d has %d taps, more than max_taps=%d" % (k, meta[k].count, max_taps))
+    return TapSet(buf, lay, n, int(max_taps), side, meta)
+
+
+def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out_side=128, dtype=torch.float16,
+                   return_offsets=False):
+    """Rasterise trajectories ([n, iters] complex128, as ``Trajectory.x``) into PSFs on ``device``.
+
+    Bit-identical to ``PSF(canvas, trajectory, [fraction]).fit()`` (+ ``centerPSF()`` + central crop + cast).
+    """
+    traj = np.ascontiguousarray(np.asarray(trajectories, dtype=np.complex128))
+    if traj.ndim == 1:
+        traj = traj[None]
+    n, iters = traj.shape
+    fr = np.ascontiguousarray(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("detectinblur_b200: PSF rasterisation runs on a CUDA device (there is no CPU path)")
+    t_traj = torch.from_numpy(traj.view(np.float64).reshape(n, iters * 2)).to(device, non_blocking=False)
+    t_fr = torch.from_numpy(fr).to(device)
+    out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
+    offs = torch.empty((n, 2), dtype=torch.int32, device=device)
+    scratch = torch.empty((n, canvas, canvas), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib.dib_rasterize_psf(ctypes.c_void_p(t_traj.data_ptr()), ctypes.c_void_p(t_fr.data_ptr()), n, iters,
+                                              int(canvas), 1 if center else 0, int(out_side), ctypes.c_void_p(out.data_ptr()),
+                                              _TORCH_TO_DIB[dtype], ctypes.c_void_p(offs.data_ptr()),
+                                              ctypes.c_void_p(scratch.data_ptr()), _stream_ptr(device)))
+    if return_offsets:
+        return out, offs
+    return out
+
+
+def checksum(tensor, out=None, accumulate=False):
+    """Order-independent 64-bit checksum of a CUDA tensor's raw element bits -> int64 CUDA tensor of one element."""
+    _require_cuda(tensor, "tensor")
+    if tensor.dtype not in _TORCH_TO_DIB:
+        raise TypeError("checksum supports float16/32/64 tensors")
+    t = tensor.contiguous()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=t.device)
+        accumulate = False
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib.dib_checksum(ctypes.c_void_p(t.data_ptr()), _TORCH_TO_DIB[t.dtype], t.numel(),
+                                         ctypes.c_void_p(out.data_ptr()), 1 if accumulate else 0, _stream_ptr(t.device)))
+    return out
