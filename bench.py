@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the motion-blur synthesis hot path (BASELINE.json metric: blurred images/sec, 800x1333 RGB).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3] [--impl reference]
+
+Own arm: one "step" blurs one batch of `--batch` synthetic 3x800x1333 fp32 images (BASELINE config 2: stored-format
+128x128 PSFs, param_index 1, low exposure) with ONE tiled-kernel launch; inputs, tap set and outputs are resident in
+HBM when the timed region starts (`value`).  `e2e` repeats the measurement through the reference-facing call
+(`blur_image_list`) with pinned HOST buffers: H2D of images + dense PSFs, tap compaction, blur, D2H of the results.
+`roofline` is the tiled kernel against the measured HBM copy bandwidth; `cpu_baseline` is the oracle's port of the
+reference's CPU Fourier blur (--cpu_blur path) on the host cores.
+
+Reference arm (`--impl reference`): the same CPU Fourier port on all host cores, same metric and config.
+Multi-GPU: one process per GPU under torchrun, images sharded by rank, no collective in the timed region (weak scaling);
+an NCCL all-gather of one checksum per rank runs after it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+H, W, C = 800, 1333, 3
+ALGO_BYTES_PER_IMAGE = 2 * C * H * W * 4          # read once + write once, fp32
+PARAMS = [0.005, 0.001, 0.00005]
+FRACTIONS = [1 / 18, 1 / 10, 1 / 5, 1 / 2, 1]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_spec(name, batch):
+    if name == "cfg2":
+        return dict(name="cfg2", batch=batch or 8, param_index=1, exposures=[0, 1, 2],
+                    desc="gpu_blur of batch %dx3x800x1333 fp32, stored-format 128x128 PSFs, param_index 1 (expl 0.005), "
+                         "low exposure (1/18, 1/10, 1/5)" % (batch or 8))
+    return dict(name="cfg3", batch=batch or 16, param_index=3, exposures=[3, 4],
+                desc="gpu_blur of batch %dx3x800x1333 fp32, 128x128 PSFs, param_index 3 (expl 0.00005), "
+                     "high exposure (1/2, 1)" % (batch or 16))
+
+
+def make_trajectories(spec, seed):
+    """Seeded camera-shake trajectories, drawn like dataset_utils/generate_PSFs.py:47-48 (Trajectory.fit().fit())."""
+    from detectinblur_b200.motion_blur.generate_trajectory import Trajectory
+    import random
+    np.random.seed(seed)
+    random.seed(seed)
+    xs, fr = [], []
+    for k in range(spec["batch"]):
+        e = spec["exposures"][k % len(spec["exposures"])]
+        tr = Trajectory(canvas=256, max_len=96, expl=PARAMS[spec["param_index"] - 1]).fit().fit()
+        xs.append(tr.x)
+        fr.append(FRACTIONS[e])
+    return np.stack(xs), np.array(fr)
+
+
+# ------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        allrows = []
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                row = (ts, float(parts[1]), float(parts[2]), parts[5:9])
+            except ValueError:
+                continue
+            allrows.append(row)
+        inside = [r for r in allrows if t0 - 0.05 <= r[0] <= t1 + 0.05] or allrows
+        for ts, s, m, flags in inside:
+            sm.append(s)
+            mx.append(m)
+            for nm, fl in zip(names, flags):
+                if fl.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    """One host core blurring `count` 800x1333 images with the reference's CPU Fourier algorithm (oracle port)."""
+    seed, count, psf = args
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        pass
+    from oracle import fourier_oracle as fo
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (H, W, C), dtype=np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(count):
+        fo.fourier_blur(img, psf)
+    return time.perf_counter() - t0
+
+
+def cpu_fourier_throughput(psf, images_per_core, pool=None, cores=None):
+    """images/s of the CPU Fourier blur with one worker per host core (mirrors DataLoader workers, train.py:203-205)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    own_pool = pool is None
+    if own_pool:
+        pool = mp.get_context("spawn").Pool(cores)
+        pool.map(_cpu_worker, [(k, 0, psf) for k in range(cores)])     # start the workers, import scipy
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, [(k, images_per_core, psf) for k in range(cores)], chunksize=1)
+    wall = time.perf_counter() - t0
+    if own_pool:
+        pool.close()
+        pool.join()
+    return cores * images_per_core / wall, wall, cores
+
+
+def baseline_psf(spec):
+    """A PSF of the workload's class for the CPU arm, from the oracle's generator (no GPU needed)."""
+    from oracle import psf_oracle as po
+    np.random.seed(1337)
+    e = spec["exposures"][-1]
+    p16, _ = po.stored_psf(PARAMS[spec["param_index"] - 1], FRACTIONS[e], np.random)
+    return po.crop128(p16).astype(np.float32)
+
+
+def run_reference_arm(args, spec):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    psf = baseline_psf(spec)
+    pool = mp.get_context("spawn").Pool(cores)
+    pool.map(_cpu_worker, [(k, 0, psf) for k in range(cores)])
+    per_core = max(1, -(-spec["batch"] // cores))        # a step = one batch spread over the host cores
+    for _ in range(args.warmup):
+        cpu_fourier_throughput(psf, per_core, pool, cores)
+    t0 = time.perf_counter()
+    n_img = 0
+    for _ in range(args.steps):
+        cpu_fourier_throughput(psf, per_core, pool, cores)
+        n_img += per_core * cores
+    wall = time.perf_counter() - t0
+    pool.close()
+    pool.join()
+    value = n_img / wall
+    line = {
+        "impl": "reference", "metric": "blurred images/sec (800x1333 RGB)", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": spec["desc"], "path": "CPU Fourier blur (motion_blur/blur_image.py port, --cpu_blur)",
+                   "images_per_step": per_core * cores},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps x %d images of 800x1333x3 uint8, one process per core, scipy fftconvolve" % (
+                             args.steps, per_core * cores)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- own arm
+def run_own_arm(args, spec):
+    import torch
+    import torch.distributed as dist
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+    from detectinblur_b200 import _lib
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = spec["batch"]
+
+    # ---- synthetic inputs: images as torch.rand (seed 1337 + rank), PSFs rasterised on the GPU from seeded trajectories
+    n_rot = 3     # rotating input batches: 3 x 102 MB of inputs (+ outputs) > 126 MB L2, nothing survives between steps
+    gen = torch.Generator(device="cpu").manual_seed(1337 + rank)
+    host_batches = [torch.rand((B, C, H, W), generator=gen).pin_memory() for _ in range(n_rot)]
+    batches = [hb.to(dev) for hb in host_batches]
+    outs = torch.empty((B, C, H, W), device=dev)
+    traj, fracs = make_trajectories(spec, seed=1337 * rank)
+    psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
+    psfs = psfs16.float()                       # stored-format values (fp16 grid) in the image dtype
+    host_psfs = psfs.cpu().pin_memory()
+    tapset = ops.compact_taps(psfs, normalize=True)
+    taps = tapset.counts
+    idx = list(range(B))
+
+    plans = [bf.prepare_blur([batches[r][i] for i in range(B)], tapset, idx, outs=[outs[i] for i in range(B)])
+             for r in range(n_rot)]
+
+    def step(k):
+        plans[k % n_rot].run()      # one dib_blur_batch call: host planning + ONE tiled-kernel launch
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = bf.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev[0].record()
+    for k in range(args.steps):
+        step(k)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    launches = bf.launch_count() - l0
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    per_step = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)])
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms / 1000.0)
+
+    # ---- kernel duration, live: the blur launch alone between events (same stream), averaged over the timed steps
+    kern_ms = float(per_step.mean())
+    algo_bytes = ALGO_BYTES_PER_IMAGE * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % spec["name"])
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- FP32 pipe probe (compute leg of the roofline: taps x pixels FMAs)
+    sink = torch.empty(148 * 8 * 256 * 2, device=dev)
+    cnt = ctypes.c_uint64(0)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(_lib.lib.dib_fp32_probe(200, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(cnt), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(_lib.lib.dib_fp32_probe(2000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(cnt), st))
+    e1.record()
+    torch.cuda.synchronize()
+    fp32_tflops = 2.0 * cnt.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    fmas = float(sum(taps)) * C * H * W
+    t_hbm = algo_bytes / (hbm_peak * 1e9)
+    t_fma = 2.0 * fmas / (fp32_tflops * 1e12)
+    roof_frac_max = max(t_hbm, t_fma) / (kern_ms * 1e-3)
+
+    # ---- end to end through the reference-facing API with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        host_out = torch.empty((B, C, H, W)).pin_memory()
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def e2e_step(k):
+            hb = host_batches[k % n_rot]
+            dbatch = hb.to(dev, non_blocking=True)
+            dpsf = host_psfs.to(dev, non_blocking=True)
+            images = [dbatch[i] for i in range(B)]
+            bf.blur_image_list(images, [{"blurring": True}] * B, [dpsf[i] for i in range(B)])
+            for i in range(B):
+                host_out[i].copy_(images[i], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for k in range(2):
+            e2e_step(k)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "images/s",
+               "h2d_bytes_per_step": int(B * C * H * W * 4 + B * 128 * 128 * 4), "d2h_bytes_per_step": int(B * C * H * W * 4),
+               "steps": e2e_steps, "api": "blur_image_list(images, blur_dicts, psfs) on pinned host buffers"}
+
+    # ---- optional cross-shard verification: all-gather one checksum per rank (outside every timed region)
+    csum = ops.checksum(outs)
+    sums = [int(csum.item()) & 0xFFFFFFFFFFFFFFFF]
+    if world > 1:
+        gathered = [torch.zeros_like(csum) for _ in range(world)]
+        dist.all_gather(gathered, csum)
+        sums = [int(g.item()) & 0xFFFFFFFFFFFFFFFF for g in gathered]
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            psf_host = host_psfs[B - 1].numpy().copy()
+            cores = os.cpu_count() or 1
+            per_core = 3
+            v, wall, cores = cpu_fourier_throughput(psf_host, per_core, None, cores)
+            cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "%d images of 800x1333x3 (%d per core, one process per core), CPU Fourier blur port "
+                             "(oracle/fourier_oracle.py), %.1f s wall" % (cores * per_core, per_core, wall)}
+        line = {
+            "metric": "blurred images/sec (800x1333 RGB)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": spec["desc"], "batch_per_gpu": B, "taps": taps,
+                       "l2": "3 rotating input batches (3 x %.0f MB in, %.0f MB out) > 126 MB L2" % (
+                           B * C * H * W * 4 / 1e6, B * C * H * W * 4 / 1e6),
+                       "parallelism": "images sharded by rank, no collective on the hot path"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "dib::blur_tiled_kernel",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                         "fp32_probe_tflops": fp32_tflops, "fma_per_launch": fmas,
+                         "t_hbm_ms": t_hbm * 1e3, "t_fp32_ms": t_fma * 1e3,
+                         "frac_of_max_roofline": roof_frac_max},
+            "cpu_baseline": cpu,
+            "checksums": ["%016x" % s for s in sums],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    spec = workload_spec(args.workload, args.batch)
+    if args.impl == "reference":
+        run_reference_arm(args, spec)
+    else:
+        run_own_arm(args, spec)
+
+
+if __name__ == "__main__":
+    main()

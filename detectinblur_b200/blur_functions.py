@@ -49,23 +49,47 @@ def pad_mode_for(psf_side, H, W):
     return _lib.PAD_REFLECT128
 
 
-def blur_batch(images, tapset, psf_indices, outs=None, noise=None, noise_sd=None, clamp=None, philox_seed=None,
-               mean=None, std=None, gamma=None, exact=None):
-    """Blur a list of CHW CUDA tensors (same dtype, any sizes) with PSFs of ``tapset``.
+class BlurPlan(object):
+    """A prepared batched blur: image descriptors built once, ``run()`` only crosses the C ABI (one call per <= 32
+    images).  ``blur_batch`` is ``prepare_blur(...).run()``; loops that re-blur the same buffers keep the plan."""
+
+    def __init__(self, descs, n, tapset, dtype, algo, philox_seed, device, results, keep):
+        self.descs, self.n, self.tapset, self.dtype, self.algo = descs, n, tapset, dtype, algo
+        self.philox_seed, self.device, self.results, self._keep = philox_seed, device, results, keep
+        self._launches = ctypes.c_int(0)
+
+    def run(self):
+        global _launch_count
+        ts = self.tapset
+        with torch.cuda.device(self.device):
+            stream = psf_ops._stream_ptr(self.device)
+            for lo in range(0, self.n, _lib.MAX_BATCH):
+                cnt = min(_lib.MAX_BATCH, self.n - lo)
+                sub = ctypes.cast(ctypes.byref(self.descs, lo * ctypes.sizeof(_lib.Image)), ctypes.POINTER(_lib.Image))
+                _lib.check(_lib.lib.dib_blur_batch(sub, cnt, ctypes.c_void_p(ts.buffer.data_ptr()) if ts is not None else None,
+                                                   ts.n_psfs if ts is not None else 0, ts.max_taps if ts is not None else 0,
+                                                   ts.meta if ts is not None else None, _DT[self.dtype], self.algo,
+                                                   int(self.philox_seed or 0), lo, ctypes.byref(self._launches), stream))
+                _launch_count += self._launches.value
+        return self.results
+
+
+def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=None, clamp=None, philox_seed=None,
+                 mean=None, std=None, gamma=None, exact=None):
+    """Build the descriptors of a batched blur of CHW CUDA tensors (same dtype, any sizes) with PSFs of ``tapset``.
 
     images       list of [C, H, W] tensors (float32 or float16, rows contiguous)
     psf_indices  per image: index into ``tapset`` or -1 (pass the image through the epilogue only)
-    outs         optional list of destination tensors ([C, H, W'] with W' >= W allowed: pitched / padded batches)
+    outs         optional list of destination tensors ([C, H, W'] views with larger pitches allowed: padded batches)
     noise        optional list of pre-drawn N(0,1) tensors (or None entries), ``noise_sd`` the matching sqrt(var)
     philox_seed  draw the noise in-kernel instead (Philox4x32-10); needs ``noise_sd``
     mean, std    optional per-image (C,) sequences: fused ``(x - mean) / std`` (net_transforms.py:135-139)
-    Returns the list of output tensors.
+    Returns a BlurPlan; ``plan.run()`` launches and returns the list of output tensors.
     """
-    global _launch_count
     n = len(images)
-    if n == 0:
-        return []
     exact = _exact_default() if exact is None else exact
+    if n == 0:
+        return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
     dev = images[0].device
     dtype = images[0].dtype
     if dtype not in _DT:
@@ -124,19 +148,12 @@ def blur_batch(images, tapset, psf_indices, outs=None, noise=None, noise_sd=None
                 d.std[c] = float(std[k][c])
         d.epilogue = epi
     algo = _lib.ALGO_GENERIC if exact else _lib.ALGO_AUTO
-    launches = ctypes.c_int(0)
-    with torch.cuda.device(dev):
-        stream = psf_ops._stream_ptr(dev)
-        for lo in range(0, n, _lib.MAX_BATCH):
-            cnt = min(_lib.MAX_BATCH, n - lo)
-            sub = ctypes.cast(ctypes.byref(descs, lo * ctypes.sizeof(_lib.Image)), ctypes.POINTER(_lib.Image))
-            _lib.check(_lib.lib.dib_blur_batch(sub, cnt, ctypes.c_void_p(tapset.buffer.data_ptr()) if tapset is not None else None,
-                                               tapset.n_psfs if tapset is not None else 0,
-                                               tapset.max_taps if tapset is not None else 0,
-                                               tapset.meta if tapset is not None else None, _DT[dtype], algo,
-                                               int(philox_seed or 0), lo, ctypes.byref(launches), stream))
-            _launch_count += launches.value
-    return results
+    return BlurPlan(descs, n, tapset, dtype, algo, philox_seed, dev, results, keep)
+
+
+def blur_batch(images, tapset, psf_indices, **kwargs):
+    """Blur a list of CHW CUDA tensors in one call; arguments as ``prepare_blur``.  Returns the output tensors."""
+    return prepare_blur(images, tapset, psf_indices, **kwargs).run()
 
 
 def _draw_effects(add_noise, noise_level, add_block, add_jpeg_artifact):

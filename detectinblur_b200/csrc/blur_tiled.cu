@@ -2,47 +2,72 @@
 //
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
-// persistent launch per batch:
-//   * work unit  = one 80 x 224 output tile of one channel of one image; each CTA owns a cost-balanced contiguous
-//                  range of tiles (host-planned, no atomics), so it mostly stays on one image / one PSF;
-//   * staging    = tile + halo of the current program chunk, moved global -> shared by TMA bulk copies
-//                  (cp.async.bulk, one per tile row: the 16-byte-aligned interior of the row segment) completing on
-//                  an mbarrier; the <= 3 unaligned floats at each row end and all reflect-101 border columns are
-//                  fetched with 4-byte cp.async from their mirrored source and arrive on the same mbarrier.
-//                  Rows are independent copies, so reflected rows cost nothing extra and the reference's native
-//                  unpitched CHW layout (row pitch 5332 B for W = 1333) needs no repacking.  Two stages are in
-//                  flight: chunk k+1 loads while chunk k is computed;
-//   * compute    = each thread owns an 8-row x 7-column register tile (lanes sit 7 floats apart in a row: odd
-//                  stride -> conflict-free scalar LDS).  Taps are consumed as the program built by taps.cu: groups
-//                  of 4 PSF columns swept row by row; a rotating 8 x 10 register window of the input slides with the
-//                  sweep, so each shared-memory load feeds ~4-10 FMAs and the kernel is FP32-pipe bound, not
-//                  LDS bound.  Absent taps inside a group are skipped with warp-uniform branches (56 FMAs each);
+// persistent, warp-specialised launch per batch:
+//   * work unit  = one 80 x 224 output tile of one channel of one image; each CTA (one per SM) owns a cost-balanced
+//                  contiguous range of tiles (host-planned, no atomics), so it mostly stays on one image / one PSF;
+//   * producer   = one warp.  For every stage (tile x program chunk) it stages tile + halo global -> shared:
+//                  TMA bulk copies (cp.async.bulk, one per tile row, the 16-byte-aligned interior of the row
+//                  segment) plus 4-byte cp.async for the <= 3 unaligned floats at each row end and for all
+//                  reflect-101 border columns, all completing on the stage's "full" mbarrier.  Rows are independent
+//                  copies, so reflected rows cost nothing extra and the reference's native unpitched CHW layout (row
+//                  pitch 5332 B for W = 1333) needs no repacking.  Two stages are in flight; the producer waits on the
+//                  stage's "empty" mbarrier before refilling it;
+//   * consumers  = eight warps (two per SM sub-partition).  Each thread owns a 10-row x 7-column register tile (lanes
+//                  sit 7 floats apart in a row: odd stride -> conflict-free scalar LDS).  Taps are consumed as the
+//                  program built by taps.cu: groups of 4 PSF columns swept row by row; a rotating 11 x 10 register
+//                  window of the input slides with the sweep (the row of the NEXT step is loaded while the current
+//                  step's FMAs issue), so each shared-memory load feeds ~5-14 FMAs and the loop is FP32-pipe bound, not
+//                  LDS bound.  Absent taps inside a group are skipped with warp-uniform branches (70 FMAs each);
 //   * epilogue   = noise / clamp / gamma / (x - mean) / std (blur_functions.py:72-74, net_transforms.py:135-139) fused
-//                  on the way out: accumulators -> shared staging (skewed to the global address phase) -> 16-byte
-//                  vector stores, scalar stores only for the <= 3 unaligned floats at each row end.
+//                  on the way out, per warp and without block-level barriers: accumulators -> the warp's private
+//                  row buffer (skewed to the global address phase) -> 16-byte vector stores, scalar stores only for
+//                  the <= 3 unaligned floats at each row end.
 // No tensor cores: the contraction is sparse and data dependent.  Results differ from the exact-order kernel only
-// by FMA contraction and tap order (measured <= 3e-7 on [0,1] images; bound 1e-5).
+// by FMA contraction and tap order (measured <= 4e-7 on [0,1] images; bound 1e-5).
 #include "dib_common.cuh"
 
 namespace dib {
 
-constexpr int kR = 8;                       // output rows per thread
+// Shape of the register tiling.  The unrolled sweep body is kR (rotations) x kGroupW (tap columns) x kR * kCC FMAs of
+// 16 bytes each, and it has to stay resident in the instruction cache: kR = 6 gives 16 KB, kR = 8 gave 29 KB and
+// spent as many cycles waiting for instruction fetch as issuing (profiles/round1_notes.md).
+#ifndef DIB_R
+#define DIB_R 6
+#endif
+#ifndef DIB_WARP_ROWS
+#define DIB_WARP_ROWS 6
+#endif
+#ifndef DIB_WARP_COLS
+#define DIB_WARP_COLS 2
+#endif
+constexpr int kR = DIB_R;                   // output rows per thread (= rotation period of the register window)
 constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
-constexpr int kWarps = 10;
-constexpr int kThreads = kWarps * 32;       // 320
-constexpr int kTH = kWarps * kR;            // 80 output rows per tile
-constexpr int kTW = 32 * kCC;               // 224 output columns per tile
+constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps are arranged kWarpRows x kWarpCols over the tile
+constexpr int kWarpCols = DIB_WARP_COLS;
+constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: equal load on the 4 SM sub-partitions
+constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
+constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
+constexpr int kProducerRegs = 40;           // setmaxnreg budgets; together they must fit the 64K-register file
+constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8 > 232
+                                 ? 232
+                                 : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
+static_assert(kComputeWarps % 4 == 0 && kR % 2 == 0, "warpgroup-aligned compute warps, rows stored in pairs");
+constexpr int kTH = kWarpRows * kR;         // 32 output rows per tile
+constexpr int kTW = kWarpCols * 32 * kCC;   // 448 output columns per tile
 constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
-constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 104
-constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 3) + 3) / 4 * 4 + 0;   // 252 floats (16 B multiple)
-constexpr int kOutPitch = kTW + 4;          // staging pitch of the output tile (skew <= 3)
+constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
+constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 3) + 3) / 4 * 4;   // 472 floats (16 B multiple)
+constexpr int kOutPitch = 32 * kCC + 4;     // one staged output row of a warp (skew <= 3)
+constexpr int kHdrBytes = 64;
 constexpr int kAuxBytes = (kChunkDataMax + 15) / 16 * 16;          // segment records + weights of one chunk
 constexpr int kRowTabBytes = ((kRowsMax * 4) + 15) / 16 * 16;
 constexpr int kTileBytes = kRowsMax * kPitch * 4;
-constexpr int kStageBytes = kAuxBytes + kRowTabBytes + kTileBytes;
-constexpr int kSmemBytes = 2 * kStageBytes + 64;                   // + 2 mbarriers
+constexpr int kStageBytes = kHdrBytes + kAuxBytes + kRowTabBytes + kTileBytes;
+constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;    // two staged rows per compute warp
+constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 64;    // + 4 mbarriers
+static_assert(kRowsMax <= kProducerWarps * 32, "one staged row per producer thread");
 static_assert(kPitch % 4 == 0 && kPitch >= kTW + kChunkGroups * kGroupW - 1 + 3, "pitch must hold tile + halo + skew");
-static_assert(kTH * kOutPitch * 4 <= kTileBytes, "output staging aliases the input tile");
+static_assert(kStageBytes % 16 == 0, "stage must keep 16-byte alignment");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 struct TiledImage {
@@ -75,6 +100,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -104,6 +132,27 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// shared-memory accesses by 32-bit shared address (no generic-pointer arithmetic in the hot loops)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_entry(uint32_t addr, float& w, int& code) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(w), "=r"(code) : "r"(addr));
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+
 __device__ __forceinline__ int reflect101(int v, int n) {
     v = v < 0 ? -v : v;
     v = v >= n ? 2 * (n - 1) - v : v;
@@ -111,6 +160,15 @@ __device__ __forceinline__ int reflect101(int v, int n) {
 }
 
 // ---------------------------------------------------------------- stage bookkeeping
+// What the producer tells the consumers about a stage (first 64 bytes of the stage's shared memory).
+struct __align__(16) StageHdr {
+    int tile;           // global tile index; -1 = no more work
+    int img, ch, i0, j0;
+    int first_chunk, last_chunk;
+    int dy_hi, dx_hi, nseg;
+};
+static_assert(sizeof(StageHdr) <= kHdrBytes, "stage header too large");
+
 struct Stage {
     int tile;       // global tile index, -1: none
     int chunk;
@@ -119,16 +177,19 @@ struct Stage {
 };
 
 struct StageSmem {
-    uint8_t* aux;       // SegRec[kChunkGroups] + float4 weights
+    StageHdr* hdr;
+    uint8_t* aux;       // SegRec slots + TapEntry list of the chunk
     int* rowtab;        // float offset of image column `cl` inside each staged row
     float* tile;
 };
 
 __device__ __forceinline__ StageSmem stage_smem(uint8_t* base, int b) {
     StageSmem s;
-    s.aux = base + (size_t)b * kStageBytes;
-    s.rowtab = reinterpret_cast<int*>(s.aux + kAuxBytes);
-    s.tile = reinterpret_cast<float*>(s.aux + kAuxBytes + kRowTabBytes);
+    uint8_t* p = base + (size_t)b * kStageBytes;
+    s.hdr = reinterpret_cast<StageHdr*>(p);
+    s.aux = p + kHdrBytes;
+    s.rowtab = reinterpret_cast<int*>(p + kHdrBytes + kAuxBytes);
+    s.tile = reinterpret_cast<float*>(p + kHdrBytes + kAuxBytes + kRowTabBytes);
     return s;
 }
 
@@ -155,7 +216,7 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
     r.dx_lo = (int16_t)(v.y & 0xffff);
     r.dx_hi = (int16_t)(v.y >> 16);
     r.nseg = (int16_t)(v.z & 0xffff);
-    r.wsteps = (int16_t)(v.z >> 16);
+    r.nentries = (int16_t)(v.z >> 16);
     r.data_off = v.w;
     return r;
 }
@@ -180,267 +241,337 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
 }
 
-// Geometry of one staged row: where it comes from and which part TMA can move.
-struct RowGeom {
-    const float* gp;    // source row pointer (column 0)
-    int xa_al, xb_al;   // 16-byte-aligned interior [xa_al, xb_al) of the in-image segment (may be empty)
-    int skew;           // extra float offset of the row in shared memory (0..3)
-};
-
-__device__ __forceinline__ RowGeom row_geom(const TiledImage& im, int ch, int img_row, int cl, int cr) {
-    RowGeom g;
-    const int s = reflect101(img_row, im.H);
-    g.gp = im.src + (int64_t)ch * im.src_cp + (int64_t)s * im.src_rp;
-    const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;
-    if (xb1 > xa) {
-        const uint32_t a0 = (uint32_t)((reinterpret_cast<uintptr_t>(g.gp + xa) >> 2) & 3u);
-        const uint32_t e0 = (uint32_t)((reinterpret_cast<uintptr_t>(g.gp + xb1) >> 2) & 3u);
-        g.xa_al = xa + (int)((4u - a0) & 3u);
-        g.xb_al = xb1 - (int)e0;
-        if (g.xb_al <= g.xa_al) g.xa_al = g.xb_al = xa;   // segment shorter than one aligned quad
-    } else {
-        g.xa_al = g.xb_al = cl;                             // nothing inside the image: all columns are mirrored
-    }
-    g.skew = (int)((uint32_t)(cl - g.xa_al) & 3u);          // makes (xa_al - cl + skew) a multiple of 4
-    return g;
-}
-
-// Issue every load of one stage: TMA bulk rows + program chunk (warp 0), cp.async fix-ups (all threads).
-__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar) {
+// Producer group (4 warps): issue every load of one stage.  Thread t owns staged row t: it places the row (skewed so
+// that the 16-byte-aligned interior of the in-image segment lands 16-byte aligned), moves that interior with one TMA
+// bulk copy and fetches the <= 3 + 3 unaligned end floats with 4-byte cp.async.  Tiles that reach past the left /
+// right image border then get their reflect-101 columns, each warp covering the rows its own lanes placed.
+__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar, int pt) {
     const TiledImage& im = p.img[st.img];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = pt & 31, pw = pt >> 5;
+    const int sr = lane * kProducerWarps + pw;                             // rows interleave over the producer warps
     const int rt = st.i0 - st.rec.dy_hi;                                  // image row of staged row 0
     const int nrows = kTH + st.rec.dy_hi - st.rec.dy_lo;
     const int cl = st.j0 - st.rec.dx_hi;                                  // image column of staged column 0
     const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;            // last staged image column
-    if (warp == 0) {
-        fence_proxy_async();   // order earlier generic-proxy accesses of this buffer before the async-proxy writes
-        uint32_t bytes = 0;
-        for (int sr = lane; sr < kRowsMax; sr += 32) {
-            if (sr < nrows) {
-                const RowGeom g = row_geom(im, st.ch, rt + sr, cl, cr);
-                const int ro = sr * kPitch + g.skew;
-                sm.rowtab[sr] = ro;
-                const uint32_t nb = (uint32_t)(g.xb_al - g.xa_al) * 4u;
-                if (nb) {
-                    tma_bulk_g2s(sm.tile + ro + (g.xa_al - cl), g.gp + g.xa_al, nb, bar);
-                    bytes += nb;
-                }
-            } else {
-                sm.rowtab[sr] = sr * kPitch;
-            }
+    const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;              // in-image part [xa, xb1)
+    const float* plane = im.src + (int64_t)st.ch * im.src_cp;
+    fence_proxy_async();   // order the consumers' generic-proxy reads of this buffer before the async-proxy writes
+    if (pt == 0) {
+        StageHdr h;
+        h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
+        h.first_chunk = (st.chunk == 0);
+        h.last_chunk = (st.chunk + 1 == im.nchunks);
+        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg;
+        *sm.hdr = h;
+    }
+    uint32_t bytes = 0;
+    const float* gp = plane;
+    int ro = sr * kPitch;
+    if (sr < nrows) {
+        const int srow = reflect101(rt + sr, im.H);
+        gp = plane + (int64_t)srow * im.src_rp;
+        int xa_al = cl, xb_al = cl;          // nothing inside the image: every column is mirrored
+        if (xb1 > xa) {
+            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 2);
+            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 3u);
+            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 3u);
+            if (xb_al <= xa_al) xa_al = xb_al = xa;      // segment shorter than one aligned quad
         }
-        if (lane == 0) {
-            const uint32_t nb = (uint32_t)(kChunkSegBytes + 16 * st.rec.wsteps);
-            const uint8_t* prog = p.prog + (size_t)im.psf_index * kProgBytes;
-            tma_bulk_g2s(sm.aux, prog + st.rec.data_off, nb, bar);
+        ro += (int)((uint32_t)(cl - xa_al) & 3u);       // skew: makes (xa_al - cl + skew) a multiple of 4
+        float* drow = sm.tile + ro - cl;                 // drow[col] addresses image column col
+        const uint32_t nb = (uint32_t)(xb_al - xa_al) * 4u;
+        if (nb) {
+            tma_bulk_g2s(drow + xa_al, gp + xa_al, nb, bar);
             bytes += nb;
         }
-        mbar_arrive_expect_tx(bar, bytes);
+        for (int col = xa; col < xa_al; ++col) cp_async_4(drow + col, gp + col);      // unaligned head
+        for (int col = xb_al; col < xb1; ++col) cp_async_4(drow + col, gp + col);     // unaligned tail
     }
-    for (int sr = warp; sr < nrows; sr += kWarps) {
-        const RowGeom g = row_geom(im, st.ch, rt + sr, cl, cr);
-        float* drow = sm.tile + sr * kPitch + g.skew;
-        const int head = g.xa_al - cl;                 // columns [cl, xa_al): unaligned head and/or left mirror
-        const int nfix = head + (cr + 1 - g.xb_al);    // + columns [xb_al, cr]: unaligned tail and/or right mirror
-        for (int k = lane; k < nfix; k += 32) {
-            const int col = k < head ? cl + k : g.xb_al + (k - head);
-            cp_async_4(drow + (col - cl), g.gp + reflect101(col, im.W));
+    if (sr < kRowsMax) sm.rowtab[sr] = ro;   // rows past a partial tile are read (results discarded): offsets stay in range
+    if (pt == 32) {
+        const uint32_t nb = (uint32_t)((kChunkSegBytes + 8 * st.rec.nentries + 15) & ~15);
+        tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, bar);
+        bytes += nb;
+    }
+    if (cl < 0 || cr >= im.W) {
+        // mirrored columns [cl, xa) and [xb1, cr]: the warp walks the rows its lanes own, lanes spread over columns
+        const int nleft = xa - cl, nright = cr + 1 - xb1;
+        for (int l = 0; l < 32; ++l) {
+            const int r2 = l * kProducerWarps + pw;
+            if (r2 >= nrows) break;
+            const float* gp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gp), l));
+            float* drow2 = sm.tile + __shfl_sync(0xffffffffu, ro, l) - cl;
+            for (int k = lane; k < nleft + nright; k += 32) {
+                const int col = k < nleft ? cl + k : xb1 + (k - nleft);
+                cp_async_4(drow2 + col, gp2 + reflect101(col, im.W));
+            }
         }
     }
+    mbar_arrive_expect_tx(bar, bytes);
     cp_async_mbar_arrive(bar);
 }
 
 // ---------------------------------------------------------------- compute
-// One sweep step: the input window holds rows (r - u) mod kR in slot order; group weights w multiply the window
-// shifted by e columns.  Absent taps (w.e == 0) are skipped; the branch is uniform across the CTA.
-template <int U>
-__device__ __forceinline__ void fma_step(float (&acc)[kR][kCC], const float (&win)[kR][kWinW], const float4 w) {
-    const float we[4] = {w.x, w.y, w.z, w.w};
+// One tap of a sweep step: weight w multiplies the window shifted by E columns.  Logical window row r sits in
+// register slot (r - U) mod kR.  Row 0 -- the row loaded at the start of this step -- is consumed last, so the 49
+// FMAs on the older rows cover that load's latency.
+template <int U, int E>
+__device__ __forceinline__ void fma_tap(float (&acc)[kR][kCC], const float (&win)[kR][kWinW], const float w) {
 #pragma unroll
-    for (int e = 0; e < kGroupW; ++e) {
-        if (we[e] != 0.0f) {
+    for (int rr = 1; rr <= kR; ++rr) {
+        const int r = rr % kR;
 #pragma unroll
-            for (int r = 0; r < kR; ++r) {
-#pragma unroll
-                for (int c = 0; c < kCC; ++c) {
-                    acc[r][c] = fmaf(we[e], win[(r - U + kR) % kR][c - e + kGroupW - 1], acc[r][c]);
-                }
-            }
-        }
+        for (int c = 0; c < kCC; ++c) acc[r][c] = fmaf(w, win[(r - U + kR) % kR][c - E + kGroupW - 1], acc[r][c]);
     }
 }
 
-__device__ __forceinline__ void load_row(float (&dst)[kWinW], const float* tile, const int* rowtab, int sr, int colbase) {
-    const float* p = tile + rowtab[sr] + colbase;
+__device__ __forceinline__ void load_row(float (&dst)[kWinW], uint32_t addr) {
 #pragma unroll
-    for (int k = 0; k < kWinW; ++k) dst[k] = p[k];
+    for (int k = 0; k < kWinW; ++k) dst[k] = lds_f32(addr + 4 * k);
 }
 
-__device__ __forceinline__ void compute_chunk(float (&acc)[kR][kCC], const StageSmem& sm, const ChunkRec& rec) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const SegRec* segs = reinterpret_cast<const SegRec*>(sm.aux);
-    const float4* wts = reinterpret_cast<const float4*>(sm.aux + kChunkSegBytes);
-    for (int sg = 0; sg < rec.nseg; ++sg) {
-        const SegRec seg = segs[sg];
-        const int colbase = kCC * lane - seg.dx0 - (kGroupW - 1) + rec.dx_hi;
-        const int sr0 = warp * kR - seg.dy0 + rec.dy_hi;      // staged row of output row 0 at step 0
-        const float4* w = wts + seg.woff;
-        const int nsteps = seg.nsteps;
+// Step s of a segment sweep, s mod kR == U: fetch the new top row into the slot the previous step freed, then
+// run this step's entries.  Returns false after the segment's last step.
+template <int U>
+__device__ __forceinline__ bool sweep_step(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
+                                           int sr0, int& s, int nsteps, uint32_t& ep, int& ro_next) {
+    if (s > 0) load_row(win[(kR - U) % kR], tile_cb + 4u * (uint32_t)ro_next);
+    ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
+    int code;
+    do {
+        float w;
+        lds_entry(ep, w, code);
+        ep += 8;
+        // two-level test on the column bits instead of a switch: no jump table (constant-bank load + BRX) per tap
+        if (!(code & kEntryGap)) {
+            if (code & 2) {
+                if (code & 1) fma_tap<U, 3>(acc, win, w); else fma_tap<U, 2>(acc, win, w);
+            } else {
+                if (code & 1) fma_tap<U, 1>(acc, win, w); else fma_tap<U, 0>(acc, win, w);
+            }
+        }
+    } while (!(code & kEntryLast));
+    ++s;
+    return s < nsteps;
+}
+
+// kR consecutive steps = one full rotation of the window registers
+template <int U>
+struct SweepRound {
+    __device__ __forceinline__ static bool run(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
+                                               int sr0, int& s, int nsteps, uint32_t& ep, int& ro_next) {
+        if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next)) return false;
+        if constexpr (U + 1 < kR)
+            return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next);
+        else
+            return true;
+    }
+};
+
+__device__ __forceinline__ void compute_chunk(float (&acc)[kR][kCC], uint32_t stage_addr, int nseg, int dy_hi, int dx_hi,
+                                              int wrow, int wcol) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t aux = stage_addr + kHdrBytes;
+    const uint32_t rowtab = aux + kAuxBytes;
+    const uint32_t tile = rowtab + kRowTabBytes;
+#pragma unroll 1
+    for (int sg = 0; sg < nseg; ++sg) {
+        int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, eoff} as two words
+        lds_entry(aux + 8u * (uint32_t)sg, reinterpret_cast<float&>(raw0), raw1);
+        const int seg_dx0 = (int)(short)(raw0 & 0xffff), seg_dy0 = raw0 >> 16;
+        const int nsteps = (int)(short)(raw1 & 0xffff), seg_eoff = raw1 >> 16;
+        const int colbase = wcol * (32 * kCC) + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
+        const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
+        const int sr0 = wrow * kR - seg_dy0 + dy_hi;      // staged row of output row 0 at step 0
+        uint32_t ep = aux + kChunkSegBytes + 8u * (uint32_t)seg_eoff;
         float win[kR][kWinW];
 #pragma unroll
-        for (int r = 0; r < kR; ++r) load_row(win[r], sm.tile, sm.rowtab, sr0 + r, colbase);
+        for (int r = 0; r < kR; ++r) load_row(win[r], tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + r)));
+        int ro_next = 0;
         int s = 0;
-        while (true) {
-#pragma unroll
-            for (int u = 0; u < kR; ++u) {
-                if (s > 0) load_row(win[(kR - u) % kR], sm.tile, sm.rowtab, sr0 - s, colbase);
-                const float4 wv = w[s];
-                switch (u) {   // u is a compile-time constant after unrolling
-                    case 0: fma_step<0>(acc, win, wv); break;
-                    case 1: fma_step<1>(acc, win, wv); break;
-                    case 2: fma_step<2>(acc, win, wv); break;
-                    case 3: fma_step<3>(acc, win, wv); break;
-                    case 4: fma_step<4>(acc, win, wv); break;
-                    case 5: fma_step<5>(acc, win, wv); break;
-                    case 6: fma_step<6>(acc, win, wv); break;
-                    default: fma_step<7>(acc, win, wv); break;
-                }
-                ++s;
-                if (s == nsteps) break;
-            }
-            if (s == nsteps) break;
+#pragma unroll 1
+        while (SweepRound<0>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next)) {
         }
     }
 }
 
-// ---------------------------------------------------------------- epilogue + store
-__device__ __forceinline__ void store_tile(const TiledParams& p, const Stage& st, float (&acc)[kR][kCC], float* stage) {
-    const TiledImage& im = p.img[st.img];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* dplane = im.dst + (int64_t)st.ch * im.dst_cp;
-    // 1. accumulators -> staging; each row is skewed so that its shared address and its global address agree mod 16 B
+// ---------------------------------------------------------------- epilogue + store (per warp, no block barrier)
+// One staged row -> global with the fused epilogue (noise / clamp / gamma / normalize).  Kept out of line: the
+// common no-epilogue path below stays small and the register-tile code is not replicated around powf / Philox.
+// `srow` is the 16-byte-aligned start of the staged row; element x of the row sits at srow[skew + x].
+__device__ __noinline__ void store_row_epilogue(const float* srow, float* g, const float* nz_row, int wv, int skew, Epilogue ep,
+                                                uint64_t seed, uint64_t stream, uint64_t pbase) {
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; 4 * k - skew < wv; k += 32) {
+        const int x0 = 4 * k - skew;
+        const float4 v = *reinterpret_cast<const float4*>(srow + 4 * k);
+        float o[4] = {v.x, v.y, v.z, v.w};
+        const bool whole = (x0 >= 0) && (x0 + 3 < wv);
 #pragma unroll
-    for (int r = 0; r < kR; ++r) {
-        const int row = warp * kR + r;
-        const float* g = dplane + (int64_t)(st.i0 + row) * im.dst_rp + st.j0;
-        const int skew = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3u);
-        float* srow = stage + row * kOutPitch + skew + kCC * lane;
-#pragma unroll
-        for (int c = 0; c < kCC; ++c) srow[c] = acc[r][c];
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j;
+            if (x >= 0 && x < wv) {
+                float nz = 0.f;
+                if (ep.flags & DIB_EPI_NOISE) nz = nz_row ? nz_row[x] : philox_normal(seed, stream, pbase + x);
+                o[j] = apply_epilogue_f32(o[j], ep, nz);
+                if (!whole) g[x] = o[j];
+            }
+        }
+        if (whole) *reinterpret_cast<float4*>(g + x0) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    __syncthreads();
-    // 2. staging -> global, rows round-robin over warps, 16-byte vectors on the aligned interior
+}
+
+// Aligned quad k of a staged row covers row elements x0 = 4k - skew .. x0 + 3: one 16-byte store when it lies
+// inside [0, wv), element-wise at the (at most two) quads that straddle an end of the row.
+__device__ __forceinline__ void store_quad(float* g, uint32_t srow, int k, int skew, int wv) {
+    const int x0 = 4 * k - skew;
+    if (x0 >= 0 && x0 + 3 < wv) {
+        *reinterpret_cast<float4*>(g + x0) = lds_v4(srow + 16u * (uint32_t)k);
+    } else if (x0 + 3 >= 0 && x0 < wv) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x0 + j >= 0 && x0 + j < wv) g[x0 + j] = lds_f32(srow + 16u * (uint32_t)k + 4u * j);
+    }
+}
+
+template <bool kEpi>
+__device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0,
+                                           float (&acc)[kR][kCC], uint32_t obuf) {
+    const int lane = threadIdx.x & 31;
+    const int wv = min(32 * kCC, im.W - col0);
     Epilogue ep;
     ep.flags = im.epilogue;
     ep.noise_sd = im.noise_sd;
     ep.gamma = im.gamma;
-    ep.mean = im.mean[st.ch & 3];
-    ep.std = im.std[st.ch & 3];
-    const int wv = min(kTW, im.W - st.j0);
-    const int hv = min(kTH, im.H - st.i0);
-    const float* nplane = im.noise ? im.noise + (int64_t)st.ch * im.dst_cp : nullptr;
-    for (int row = warp; row < hv; row += kWarps) {
-        const int64_t goff = (int64_t)(st.i0 + row) * im.dst_rp + st.j0;
-        float* g = dplane + goff;
-        const int skew = (int)((reinterpret_cast<uintptr_t>(g) >> 2) & 3u);
-        const float* srow = stage + row * kOutPitch + skew;
-        const int head = min((4 - skew) & 3, wv);
-        const int nvec = (wv - head) >> 2;
-        const int tail = wv - head - 4 * nvec;
-        const uint64_t pbase = ((uint64_t)st.ch * im.H + (st.i0 + row)) * im.W + st.j0;
-        for (int q = lane; q < nvec; q += 32) {
-            const int x = head + 4 * q;
-            float4 v = *reinterpret_cast<const float4*>(srow + x);
-            if (ep.flags) {
-                float nz[4] = {0.f, 0.f, 0.f, 0.f};
-                if (ep.flags & DIB_EPI_NOISE) {
-                    if (nplane) {   // the noise tensor has its own base address: no 16-byte alignment to rely on
+    ep.mean = im.mean[ch & 3];
+    ep.std = im.std[ch & 3];
+    float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
+    const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
+    uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
+    const uint32_t rp_lo = (uint32_t)im.dst_rp;
+    const int nrows = min(kR, im.H - row0);
+    // two rows per pass: accumulators -> the warp's two row buffers (each skewed so that shared and global addresses
+    // agree mod 16 bytes: element x of a row sits at buffer[skew + x]), then 16-byte stores of both rows
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) nz[k] = nplane[goff + x + k];
-                    } else {
+    for (int r = 0; r < kR; r += 2) {
+        const int skew0 = (int)(phase & 3u), skew1 = (int)((phase + rp_lo) & 3u);
+        const uint32_t b0 = obuf, b1 = obuf + 4u * kOutPitch;
+        if (r < nrows) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            nz[k] = philox_normal(p.philox_seed, p.philox_offset + (uint64_t)im.philox_slot, pbase + x + k);
-                    }
-                }
-                v.x = apply_epilogue_f32(v.x, ep, nz[0]);
-                v.y = apply_epilogue_f32(v.y, ep, nz[1]);
-                v.z = apply_epilogue_f32(v.z, ep, nz[2]);
-                v.w = apply_epilogue_f32(v.w, ep, nz[3]);
-            }
-            *reinterpret_cast<float4*>(g + x) = v;
+            for (int c = 0; c < kCC; ++c) sts_f32(b0 + 4u * (uint32_t)(skew0 + kCC * lane + c), acc[r][c]);
         }
-        if (lane < head + tail) {
-            const int x = lane < head ? lane : head + 4 * nvec + (lane - head);
-            float v = srow[x];
-            if (ep.flags) {
-                float nz = 0.f;
-                if (ep.flags & DIB_EPI_NOISE)
-                    nz = nplane ? nplane[goff + x]
-                                : philox_normal(p.philox_seed, p.philox_offset + (uint64_t)im.philox_slot, pbase + x);
-                v = apply_epilogue_f32(v, ep, nz);
-            }
-            g[x] = v;
+        if (r + 1 < nrows) {
+#pragma unroll
+            for (int c = 0; c < kCC; ++c) sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), acc[r + 1][c]);
         }
+        __syncwarp();
+        float* g1 = g + im.dst_rp;
+        if (!kEpi) {
+            if (r < nrows) {
+                store_quad(g, b0, lane, skew0, wv);
+                store_quad(g, b0, lane + 32, skew0, wv);
+            }
+            if (r + 1 < nrows) {
+                store_quad(g1, b1, lane, skew1, wv);
+                store_quad(g1, b1, lane + 32, skew1, wv);
+            }
+        } else {
+            const uint64_t stream = p.philox_offset + (uint64_t)im.philox_slot;
+            const float* sm0 = reinterpret_cast<const float*>(__cvta_shared_to_generic(b0));
+            if (r < nrows)
+                store_row_epilogue(sm0, g, nz_row, wv, skew0, ep, p.philox_seed, stream,
+                                   ((uint64_t)ch * im.H + (row0 + r)) * im.W + col0);
+            if (r + 1 < nrows)
+                store_row_epilogue(sm0 + kOutPitch, g1, nz_row ? nz_row + im.dst_rp : nullptr, wv, skew1, ep, p.philox_seed, stream,
+                                   ((uint64_t)ch * im.H + (row0 + r + 1)) * im.W + col0);
+        }
+        __syncwarp();
+        g += 2 * im.dst_rp;
+        if (nz_row) nz_row += 2 * im.dst_rp;
+        phase += 2u * rp_lo;
     }
 }
 
 // ---------------------------------------------------------------- kernel
+// kEpi selects the variant with the fused epilogue; batches without one run the leaner instantiation.
+template <bool kEpi>
 __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
+    float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
+    uint64_t* full = bars;          // [2] producers -> consumers: stage loaded
+    uint64_t* empty = bars + 2;     // [2] consumers -> producers: stage may be refilled
     const int tile_begin = p.cta_begin[blockIdx.x], tile_end = p.cta_begin[blockIdx.x + 1];
     if (tile_begin >= tile_end) return;
+    const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bars[0], kThreads + 32);
-        mbar_init(&bars[1], kThreads + 32);
+        mbar_init(&full[0], 2 * kProducerWarps * 32);   // per producer thread: one arrive.expect_tx + one cp.async arrive
+        mbar_init(&full[1], 2 * kProducerWarps * 32);
+        mbar_init(&empty[0], kComputeWarps);
+        mbar_init(&empty[1], kComputeWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // row tables must always hold in-range offsets (rows past a partial tile are read, their results discarded)
-    for (int b = 0; b < 2; ++b) {
-        StageSmem s = stage_smem(smem, b);
-        for (int k = threadIdx.x; k < kRowsMax; k += kThreads) s.rowtab[k] = k * kPitch;
     }
     __syncthreads();
 
-    Stage cur, nxt;
-    cur.tile = tile_begin;
-    cur.chunk = 0;
-    decode_tile(p, cur.tile, cur);
-    cur.rec = load_chunk_rec(p, cur.img, 0);
-    next_stage(p, cur, tile_end, nxt);
-    issue_stage(p, cur, stage_smem(smem, 0), &bars[0]);
-
-    float acc[kR][kCC];
-    uint32_t phase[2] = {0u, 0u};
-    int b = 0;
-    while (cur.tile >= 0) {
-        // prefetch: loads of the next stage go to the other buffer; its successor's chunk record is fetched now
-        Stage nxt2;
-        if (nxt.tile >= 0) issue_stage(p, nxt, stage_smem(smem, b ^ 1), &bars[b ^ 1]);
-        next_stage(p, nxt, tile_end, nxt2);
-
-        if (cur.chunk == 0) {
-#pragma unroll
-            for (int r = 0; r < kR; ++r)
-#pragma unroll
-                for (int c = 0; c < kCC; ++c) acc[r][c] = 0.0f;
+    // Register budget: the launch splits the register file evenly over all warps; the producer warpgroup hands most of
+    // its share back so that the compute warps can hold kR * kCC accumulators + kR * kWinW window values per thread.
+    if (warp >= kComputeWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        // ------------------------------------------------ producer warpgroup
+        const int pt = threadIdx.x - kComputeWarps * 32;
+        Stage cur, nxt;
+        cur.tile = tile_begin;
+        cur.chunk = 0;
+        decode_tile(p, cur.tile, cur);
+        cur.rec = load_chunk_rec(p, cur.img, 0);
+        for (int n = 0;; ++n) {
+            const int b = n & 1;
+            next_stage(p, cur, tile_end, nxt);                        // its chunk record is in flight during the issue below
+            if (n >= 2) mbar_wait(&empty[b], ((n >> 1) - 1) & 1);    // consumers released the stage that used this buffer
+            const StageSmem sm = stage_smem(smem, b);
+            if (cur.tile < 0) {
+                if (pt == 0) sm.hdr->tile = -1;
+                mbar_arrive_expect_tx(&full[b], 0);
+                cp_async_mbar_arrive(&full[b]);
+                break;
+            }
+            issue_stage(p, cur, sm, &full[b], pt);
+            cur = nxt;
         }
-        const StageSmem sm = stage_smem(smem, b);
-        mbar_wait(&bars[b], phase[b]);
-        phase[b] ^= 1u;
-        const bool active = (cur.i0 + (int)(threadIdx.x >> 5) * kR) < p.img[cur.img].H;   // warp-uniform
-        if (active) compute_chunk(acc, sm, cur.rec);
-        __syncthreads();                       // every warp is done reading this stage
-        if (cur.chunk + 1 == p.img[cur.img].nchunks) {
-            store_tile(p, cur, acc, sm.tile);
-            __syncthreads();                   // staging consumed: the buffer may be refilled
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
+        // ------------------------------------------------ compute warps
+        const int wrow = warp / kWarpCols, wcol = warp % kWarpCols;
+        float acc[kR][kCC];
+        const uint32_t obuf = smem_u32(obuf_all + warp * 2 * kOutPitch);
+        for (int n = 0;; ++n) {
+            const int b = n & 1;
+            const StageSmem sm = stage_smem(smem, b);
+            mbar_wait(&full[b], (n >> 1) & 1);
+            StageHdr h;
+            {   // explicit vector loads keep the header in registers
+                const int4 a = reinterpret_cast<const int4*>(sm.hdr)[0], b4 = reinterpret_cast<const int4*>(sm.hdr)[1];
+                const int2 c2 = reinterpret_cast<const int2*>(sm.hdr)[4];
+                h.tile = a.x; h.img = a.y; h.ch = a.z; h.i0 = a.w;
+                h.j0 = b4.x; h.first_chunk = b4.y; h.last_chunk = b4.z; h.dy_hi = b4.w;
+                h.dx_hi = c2.x; h.nseg = c2.y;
+            }
+            if (h.tile < 0) break;
+            if (h.first_chunk) {
+#pragma unroll
+                for (int r = 0; r < kR; ++r)
+#pragma unroll
+                    for (int c = 0; c < kCC; ++c) acc[r][c] = 0.0f;
+            }
+            const TiledImage& im = p.img[h.img];
+            const int row0 = h.i0 + wrow * kR, col0 = h.j0 + wcol * (32 * kCC);
+            const bool active = row0 < im.H && col0 < im.W;                       // warp-uniform
+            if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
+            if (h.last_chunk && active) store_rows<kEpi>(p, im, h.ch, row0, col0, acc, obuf);
         }
-        cur = nxt;
-        nxt = nxt2;
-        b ^= 1;
     }
 }
 
@@ -459,7 +590,8 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     DIB_CUDA(cudaGetDevice(&dev));
     if (attr_set_dev != dev) {
         DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set_dev = dev;
     }
     TiledParams p;
@@ -521,7 +653,12 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         }
         for (int k = b + 1; k <= grid; ++k) p.cta_begin[k] = total;
     }
-    blur_tiled_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+    bool any_epi = false;
+    for (int k = 0; k < n_sel; ++k) any_epi |= (p.img[k].epilogue != 0);
+    if (any_epi)
+        blur_tiled_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+    else
+        blur_tiled_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;
 }

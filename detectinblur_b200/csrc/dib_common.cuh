@@ -31,30 +31,38 @@ void set_error(const char* fmt, ...);
 
 // ---- tap set layout (see include/dib.h) ----
 // Tiled-kernel program of one PSF (built by taps.cu, executed by blur_tiled.cu).  The PSF support is cut into
-// groups of kGroupW columns; a SEGMENT is one group's run of rows [dy0, dy0 + nsteps) with one kGroupW-wide
-// weight vector per row (zeros where the PSF has no tap).  Segments are packed into CHUNKS whose tap extents are
-// bounded (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that tile + halo of any chunk fits the
-// kernel's fixed shared-memory stage, whatever the PSF's overall extent.
-constexpr int kGroupW = 4;              // PSF columns per group (one float4 of weights per step)
-constexpr int kChunkGroups = 6;         // groups per chunk  -> column halo <= 23
-constexpr int kChunkHaloRows = 24;      // dy_hi - dy_lo per chunk
+// groups of kGroupW columns; a SEGMENT is one group's run of rows [dy0, dy0 + nsteps).  The kernel sweeps a segment
+// row by row ("steps"); for every step the program lists the taps present as ENTRIES (weight, column-in-group), so
+// the kernel never tests for absent taps.  Segments are packed into CHUNKS whose tap extents are bounded
+// (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that tile + halo of any chunk fits the kernel's fixed
+// shared-memory stage, whatever the PSF's overall extent.
+constexpr int kGroupW = 4;              // PSF columns per group
+constexpr int kChunkGroups = 5;         // groups per chunk  -> column halo <= 19
+constexpr int kChunkHaloRows = 17;      // dy_hi - dy_lo per chunk
 constexpr int kProgMaxChunks = 32;
 struct SegRec {         // 8 bytes
     int16_t dx0;        // first tap column of the group, relative to the PSF centre (tap dx = x - centre)
     int16_t dy0;        // first tap row of the run, relative to the centre
     int16_t nsteps;     // rows in the run
-    int16_t woff;       // index of the run's first weight vector inside the chunk's weight array
+    int16_t eoff;       // index of the run's first entry inside the chunk's entry array
 };
+struct TapEntry {       // 8 bytes
+    float w;            // normalised tap weight
+    int32_t code;       // bits 0-2: column inside the group (0..3) or kEntryGap; bit 3: last entry of its step
+};
+constexpr int kEntryGap = 4;            // a step without taps (a hole inside the run): nothing to accumulate
+constexpr int kEntryLast = 8;
 struct ChunkRec {       // 16 bytes
     int16_t dy_lo, dy_hi;   // tap row range of the chunk (relative to the centre)
     int16_t dx_lo, dx_hi;   // tap column range: first group's dx0 .. last group's dx0 + kGroupW - 1
     int16_t nseg;           // segments in the chunk (<= kChunkGroups)
-    int16_t wsteps;         // weight vectors in the chunk
+    int16_t nentries;       // entries in the chunk
     int32_t data_off;       // byte offset of the chunk's data block inside the PSF's program section
 };
-// chunk data block: SegRec[kChunkGroups] (48 B, fixed) then float4[wsteps]
+// chunk data block: SegRec slots (48 B, fixed) then TapEntry[nentries]
 constexpr int kChunkSegBytes = 48;
-constexpr int kChunkDataMax = kChunkSegBytes + 16 * kChunkGroups * (kChunkHaloRows + 1);   // 2448
+constexpr int kChunkMaxEntries = kChunkGroups * kGroupW * (kChunkHaloRows + 1);          // 420
+constexpr int kChunkDataMax = kChunkSegBytes + 8 * kChunkMaxEntries;                      // 3408
 constexpr size_t kProgHeaderBytes = sizeof(ChunkRec) * kProgMaxChunks;                    // 512
 constexpr size_t kProgDataBytes = 16384;
 constexpr size_t kProgBytes = kProgHeaderBytes + kProgDataBytes;

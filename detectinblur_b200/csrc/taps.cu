@@ -84,7 +84,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ unsigned sh_occ[32 * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
     __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
-    __shared__ int sh_nchunks, sh_total_steps;
+    __shared__ int sh_segcount[kProgMaxChunks * kChunkGroups];
+    __shared__ int sh_nchunks, sh_nsegs, sh_total_steps;
 
     const int n = blockIdx.x;
     const T* psf = psfs + (int64_t)n * psf_stride;
@@ -169,16 +170,18 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const bool want_prog = side <= 129 && count > 0 && ymax <= 126 && xmax <= 126;
     if (tid == 0) {
         sh_nchunks = 0;
+        sh_nsegs = 0;
         sh_total_steps = 0;
     }
     __syncthreads();
     if (want_prog) {
         const int ngroups = (xmax - xmin + kGroupW) / kGroupW;   // <= 32 for side <= 129
+        const int nrows_box = ymax - ymin + 1;
         // 3a. per group: bitmask of the PSF rows holding a tap in the group's columns (rows 0..127 -> 4 words)
         for (int k = tid; k < ngroups * 4; k += kCompactThreads) sh_occ[k] = 0u;
         __syncthreads();
-        for (int k = tid; k < ngroups * (ymax - ymin + 1); k += kCompactThreads) {
-            const int g = k / (ymax - ymin + 1), y = ymin + k % (ymax - ymin + 1);
+        for (int k = tid; k < ngroups * nrows_box; k += kCompactThreads) {
+            const int g = k / nrows_box, y = ymin + k % nrows_box;
             bool any = false;
             for (int e = 0; e < kGroupW; ++e) {
                 const int x = xmin + g * kGroupW + e;
@@ -191,16 +194,15 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
         }
         __syncthreads();
-        // 3b. one thread packs segments into chunks (a few dozen iterations of bit scans)
+        // 3b. one thread cuts the support into chunks of segments (a few dozen iterations of bit scans)
         if (tid == 0) {
-            int nchunks = 0, data_off = (int)kProgHeaderBytes, total_steps = 0;
+            int nchunks = 0, nsegs = 0;
             bool ok = true;
             for (int g0 = 0; g0 < ngroups && ok; g0 += kChunkGroups) {
                 const int g1 = min(g0 + kChunkGroups, ngroups);
                 int cursor = ymin;
                 while (ok) {
-                    // first occupied row >= cursor in this band of groups
-                    int y0 = -1;
+                    int y0 = -1;   // first occupied row >= cursor in this band of groups
                     for (int y = cursor; y <= ymax && y0 < 0; ++y)
                         for (int g = g0; g < g1; ++g)
                             if ((sh_occ[g * 4 + (y >> 5)] >> (y & 31)) & 1u) { y0 = y; break; }
@@ -208,8 +210,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                     const int y1 = min(y0 + kChunkHaloRows, ymax);
                     if (nchunks >= kProgMaxChunks) { ok = false; break; }
                     ChunkRec c;
-                    SegRec segs[kChunkGroups];
-                    int nseg = 0, wsteps = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
+                    int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
                     for (int g = g0; g < g1; ++g) {
                         int f = -1, l = -1;
                         for (int y = y0; y <= y1; ++y)
@@ -219,54 +220,110 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                         sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
                         sg.dy0 = (int16_t)(f - centre);
                         sg.nsteps = (int16_t)(l - f + 1);
-                        sg.woff = (int16_t)wsteps;
-                        wsteps += l - f + 1;
+                        sg.eoff = 0;
                         lo = min(lo, f - centre);
                         hi = max(hi, l - centre);
                         xlo = min(xlo, (int)sg.dx0);
                         xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
-                        segs[nseg++] = sg;
+                        sh_segs[nchunks * kChunkGroups + nseg] = sg;
+                        ++nseg;
+                        ++nsegs;
                     }
-                    const int bytes = kChunkSegBytes + 16 * wsteps;
-                    if (data_off + bytes > (int)kProgBytes) { ok = false; break; }
                     c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
                     c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
-                    c.nseg = (int16_t)nseg; c.wsteps = (int16_t)wsteps;
-                    c.data_off = data_off;
-                    out_chunks[nchunks] = c;
+                    c.nseg = (int16_t)nseg; c.nentries = 0;
+                    c.data_off = 0;
                     sh_chunks[nchunks] = c;
-                    SegRec* dst = reinterpret_cast<SegRec*>(my_prog + data_off);
-                    for (int k = 0; k < kChunkGroups; ++k) {
-                        SegRec z; z.dx0 = 0; z.dy0 = 0; z.nsteps = 0; z.woff = 0;
-                        dst[k] = k < nseg ? segs[k] : z;
-                        sh_segs[nchunks * kChunkGroups + k] = k < nseg ? segs[k] : z;
-                    }
-                    data_off += bytes;
-                    total_steps += wsteps;
                     ++nchunks;
                     cursor = y1 + 1;
                 }
             }
             sh_nchunks = ok ? nchunks : -1;
-            sh_total_steps = total_steps;
+            sh_nsegs = nsegs;
         }
         __syncthreads();
-        // 3c. all threads fill the weight vectors
-        const int nchunks = sh_nchunks;
-        for (int ci = 0; ci < nchunks; ++ci) {
-            const ChunkRec c = sh_chunks[ci];
-            float* wout = reinterpret_cast<float*>(my_prog + c.data_off + kChunkSegBytes);
-            for (int sgi = 0; sgi < c.nseg; ++sgi) {
-                const SegRec sg = sh_segs[ci * kChunkGroups + sgi];
-                for (int k = tid; k < sg.nsteps * kGroupW; k += kCompactThreads) {
-                    const int step = k / kGroupW, e = k % kGroupW;
-                    const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
-                    float w = 0.0f;
-                    if (x < side) {
-                        const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
-                        w = normalize ? PsfNum<T>::normalized(v, s) : v;
+        int nchunks = sh_nchunks;
+        // 3c. one thread per segment counts its entries: per step the taps present, or one gap entry
+        if (nchunks > 0) {
+            for (int k = tid; k < nchunks * kChunkGroups; k += kCompactThreads) {
+                const int ci = k / kChunkGroups, sgi = k % kChunkGroups;
+                int cnt = 0;
+                if (sgi < sh_chunks[ci].nseg) {
+                    const SegRec sg = sh_segs[k];
+                    for (int st = 0; st < sg.nsteps; ++st) {
+                        int nz = 0;
+                        for (int e = 0; e < kGroupW; ++e) {
+                            const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + st;
+                            if (x < side) {
+                                const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                                const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                                nz += (w != 0.0f);
+                            }
+                        }
+                        cnt += nz ? nz : 1;
                     }
-                    wout[(sg.woff + step) * kGroupW + e] = w;
+                }
+                sh_segcount[k] = cnt;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int data_off = (int)kProgHeaderBytes, total_steps = 0;
+                bool ok = true;
+                for (int ci = 0; ci < nchunks && ok; ++ci) {
+                    int ne = 0;
+                    for (int sgi = 0; sgi < sh_chunks[ci].nseg; ++sgi) {
+                        sh_segs[ci * kChunkGroups + sgi].eoff = (int16_t)ne;
+                        ne += sh_segcount[ci * kChunkGroups + sgi];
+                        total_steps += sh_segs[ci * kChunkGroups + sgi].nsteps;
+                    }
+                    const int bytes = kChunkSegBytes + 8 * ne;
+                    if (ne > kChunkMaxEntries || data_off + bytes > (int)kProgBytes) { ok = false; break; }
+                    sh_chunks[ci].nentries = (int16_t)ne;
+                    sh_chunks[ci].data_off = data_off;
+                    data_off += (bytes + 15) & ~15;
+                }
+                if (!ok) sh_nchunks = -1;
+                sh_total_steps = total_steps;
+            }
+            __syncthreads();
+            nchunks = sh_nchunks;
+        }
+        // 3d. write chunk records, segment records and entries
+        if (nchunks > 0) {
+            for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
+            for (int k = tid; k < nchunks * kChunkGroups; k += kCompactThreads) {
+                const int ci = k / kChunkGroups, sgi = k % kChunkGroups;
+                const ChunkRec c = sh_chunks[ci];
+                SegRec* seg_out = reinterpret_cast<SegRec*>(my_prog + c.data_off);
+                SegRec sg;
+                sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.eoff = 0;
+                if (sgi < c.nseg) sg = sh_segs[k];
+                seg_out[sgi] = sg;
+                if (sgi >= c.nseg) continue;
+                TapEntry* ent = reinterpret_cast<TapEntry*>(my_prog + c.data_off + kChunkSegBytes) + sg.eoff;
+                int pos = 0;
+                for (int st = 0; st < sg.nsteps; ++st) {
+                    int first = pos;
+                    for (int e = 0; e < kGroupW; ++e) {
+                        const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + st;
+                        if (x < side) {
+                            const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                            if (w != 0.0f) {
+                                TapEntry t;
+                                t.w = w;
+                                t.code = e;
+                                ent[pos++] = t;
+                            }
+                        }
+                    }
+                    if (pos == first) {
+                        TapEntry t;
+                        t.w = 0.0f;
+                        t.code = kEntryGap;
+                        ent[pos++] = t;
+                    }
+                    ent[pos - 1].code |= kEntryLast;
                 }
             }
         }

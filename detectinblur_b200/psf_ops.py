@@ -116,7 +116,7 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
     if traj.ndim == 1:
         traj = traj[None]
     n, iters = traj.shape
-    fr = np.ascontiguousarray(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
+    fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("detectinblur_b200: PSF rasterisation runs on a CUDA device (there is no CPU path)")
