@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdib.so")
+# DIB_LIB_PATH lets kernel experiments point at an alternative build of the same ABI (never a different backend)
+LIB_PATH = os.environ.get("DIB_LIB_PATH") or os.path.join(_HERE, "libdib.so")
 
 DIB_F32, DIB_F16, DIB_F64 = 0, 1, 2
 PAD_REFLECT128, PAD_ZERO128, PAD_REPLICATE256 = 0, 1, 2
@@ -38,6 +39,7 @@ class PsfMeta(ctypes.Structure):
         ("prog_chunks", ctypes.c_int32),
         ("prog_steps", ctypes.c_int32),
         ("flags", ctypes.c_int32),
+        ("prog_segs", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("sy", ctypes.c_double), ("sx", ctypes.c_double),
         ("syy", ctypes.c_double), ("sxx", ctypes.c_double), ("sxy", ctypes.c_double),
     ]
@@ -45,7 +47,7 @@ class PsfMeta(ctypes.Structure):
 
 class TapsetLayout(ctypes.Structure):
     _fields_ = [("meta_offset", ctypes.c_size_t), ("taps_offset", ctypes.c_size_t), ("prog_offset", ctypes.c_size_t),
-                ("prog_bytes_per_psf", ctypes.c_size_t), ("total_bytes", ctypes.c_size_t)]
+                ("prog_bytes_per_psf", ctypes.c_size_t), ("sched_offset", ctypes.c_size_t), ("total_bytes", ctypes.c_size_t)]
 
 
 class Image(ctypes.Structure):

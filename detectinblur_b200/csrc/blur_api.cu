@@ -9,7 +9,7 @@ namespace dib {
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
                    int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 uint64_t seed, uint64_t offset, cudaStream_t st);
+                 SchedWords* sched, uint64_t seed, uint64_t offset, cudaStream_t st);
 
 static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
     if (meta_host == nullptr || io_dtype != DIB_F32 || im.psf_index < 0) return false;
@@ -21,7 +21,7 @@ static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, i
 }
 }  // namespace dib
 
-extern "C" int dib_blur_batch(const dib_image* images, int n_images, const void* tapset, int n_psfs, int max_taps,
+extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapset, int n_psfs, int max_taps,
                               const dib_psf_meta* meta_host, int io_dtype, int algo, uint64_t philox_seed,
                               uint64_t philox_offset, int* launches, void* stream) {
     using namespace dib;
@@ -53,10 +53,11 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, const void*
     }
     DIB_CHECK_ARG(!any_psf || (tapset != nullptr && n_psfs > 0 && max_taps > 0), "dib_blur_batch: tap set missing");
     const dib_tapset_layout L = tapset_layout(n_psfs > 0 ? n_psfs : 1, max_taps > 0 ? max_taps : 1);
-    const uint8_t* base = static_cast<const uint8_t*>(tapset);
+    uint8_t* base = static_cast<uint8_t*>(tapset);
     const dib_psf_meta* meta_dev = reinterpret_cast<const dib_psf_meta*>(base + L.meta_offset);
     const dib_tap* taps = reinterpret_cast<const dib_tap*>(base + L.taps_offset);
     const uint8_t* prog = base + L.prog_offset;
+    SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     // split the batch: tiled kernel where eligible (heaviest PSFs first), exact-order kernel for the rest
@@ -74,7 +75,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, const void*
                 return DIB_ERR_UNSUPPORTED;
             }
         }
-        // insertion sort by tap count, descending (stable): long tiles are scheduled first
+        // insertion sort by tap count, descending (stable): the dynamic scheduler hands out long tiles first
         for (int a = 1; a < n_sel; ++a) {
             const int v = order[a];
             const int cv = meta_host[images[v].psf_index].count;
@@ -88,7 +89,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, const void*
     }
     int nl = 0;
     if (n_sel > 0) {
-        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, philox_seed, philox_offset, st);
+        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

@@ -3,8 +3,8 @@
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
 // persistent, warp-specialised launch per batch:
-//   * work unit  = one 80 x 224 output tile of one channel of one image; each CTA (one per SM) owns a cost-balanced
-//                  contiguous range of tiles (host-planned, no atomics), so it mostly stays on one image / one PSF;
+//   * work unit  = one 36 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
+//                  global ticket counter, images with the heaviest PSFs first;
 //   * producer   = one warp.  For every stage (tile x program chunk) it stages tile + halo global -> shared:
 //                  TMA bulk copies (cp.async.bulk, one per tile row, the 16-byte-aligned interior of the row
 //                  segment) plus 4-byte cp.async for the <= 3 unaligned floats at each row end and for all
@@ -64,7 +64,7 @@ constexpr int kRowTabBytes = ((kRowsMax * 4) + 15) / 16 * 16;
 constexpr int kTileBytes = kRowsMax * kPitch * 4;
 constexpr int kStageBytes = kHdrBytes + kAuxBytes + kRowTabBytes + kTileBytes;
 constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;    // two staged rows per compute warp
-constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 64;    // + 4 mbarriers
+constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 64;    // + 4 mbarriers + 2 tile-ticket slots
 static_assert(kRowsMax <= kProducerWarps * 32, "one staged row per producer thread");
 static_assert(kPitch % 4 == 0 && kPitch >= kTW + kChunkGroups * kGroupW - 1 + 3, "pitch must hold tile + halo + skew");
 static_assert(kStageBytes % 16 == 0, "stage must keep 16-byte alignment");
@@ -91,7 +91,7 @@ struct TiledParams {
     int n_images;
     int total_tiles;
     uint64_t philox_seed, philox_offset;
-    int cta_begin[160];           // tile range of CTA b = [cta_begin[b], cta_begin[b+1])
+    SchedWords* sched;            // dynamic tile scheduler (tap set buffer): tiles are handed out in index order
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -111,11 +111,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
+#ifdef DIB_NO_HINT
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#endif
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware, do not spin
 }
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -178,7 +182,7 @@ struct Stage {
 
 struct StageSmem {
     StageHdr* hdr;
-    uint8_t* aux;       // SegRec slots + TapEntry list of the chunk
+    uint8_t* aux;       // SegRec slots + weight vectors of the chunk
     int* rowtab;        // float offset of image column `cl` inside each staged row
     float* tile;
 };
@@ -216,13 +220,26 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
     r.dx_lo = (int16_t)(v.y & 0xffff);
     r.dx_hi = (int16_t)(v.y >> 16);
     r.nseg = (int16_t)(v.z & 0xffff);
-    r.nentries = (int16_t)(v.z >> 16);
+    r.wsteps = (int16_t)(v.z >> 16);
     r.data_off = v.w;
     return r;
 }
 
-// successor of a stage within [.., tile_end): next chunk of the same tile, else chunk 0 of the next tile
-__device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cur, int tile_end, Stage& nx) {
+// Hand the producer group its next tile.  Thread 0 of the group takes a ticket from the global counter and shares
+// it through shared memory; the two slots alternate so one named barrier per fetch is enough.
+__device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int& nfetch, int pt) {
+    int* slot = slots + (nfetch & 1);
+    if (pt == 0) {
+        const unsigned t = atomicAdd(&p.sched->next_tile, 1u);
+        *slot = t < (unsigned)p.total_tiles ? (int)t : -1;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+    ++nfetch;
+    return *slot;
+}
+
+// successor of a stage: next chunk of the same tile, else chunk 0 of the next tile the scheduler hands out
+__device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cur, Stage& nx, int* slots, int& nfetch, int pt) {
     if (cur.tile < 0) {
         nx.tile = -1;
         return;
@@ -230,13 +247,11 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
     if (cur.chunk + 1 < p.img[cur.img].nchunks) {
         nx = cur;
         nx.chunk = cur.chunk + 1;
-    } else if (cur.tile + 1 < tile_end) {
-        nx.tile = cur.tile + 1;
+    } else {
+        nx.tile = fetch_tile(p, slots, nfetch, pt);
+        if (nx.tile < 0) return;
         nx.chunk = 0;
         decode_tile(p, nx.tile, nx);
-    } else {
-        nx.tile = -1;
-        return;
     }
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
 }
@@ -289,7 +304,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
     if (sr < kRowsMax) sm.rowtab[sr] = ro;   // rows past a partial tile are read (results discarded): offsets stay in range
     if (pt == 32) {
-        const uint32_t nb = (uint32_t)((kChunkSegBytes + 8 * st.rec.nentries + 15) & ~15);
+        const uint32_t nb = (uint32_t)(kChunkSegBytes + 16 * (st.rec.wsteps + 1));
         tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, bar);
         bytes += nb;
     }
@@ -313,8 +328,8 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
 
 // ---------------------------------------------------------------- compute
 // One tap of a sweep step: weight w multiplies the window shifted by E columns.  Logical window row r sits in
-// register slot (r - U) mod kR.  Row 0 -- the row loaded at the start of this step -- is consumed last, so the 49
-// FMAs on the older rows cover that load's latency.
+// register slot (r - U) mod kR.  Row 0 -- the row loaded at the start of this step -- is consumed last, so the FMAs
+// on the older rows cover that load's latency.
 template <int U, int E>
 __device__ __forceinline__ void fma_tap(float (&acc)[kR][kCC], const float (&win)[kR][kWinW], const float w) {
 #pragma unroll
@@ -330,27 +345,28 @@ __device__ __forceinline__ void load_row(float (&dst)[kWinW], uint32_t addr) {
     for (int k = 0; k < kWinW; ++k) dst[k] = lds_f32(addr + 4 * k);
 }
 
-// Step s of a segment sweep, s mod kR == U: fetch the new top row into the slot the previous step freed, then
-// run this step's entries.  Returns false after the segment's last step.
+// Step s of a segment sweep, s mod kR == U: fetch the new top row into the slot the previous step freed and the
+// NEXT step's weight vector (kR is even, so the two weight registers simply alternate), then accumulate the taps
+// present in this step's vector; absent taps are skipped with warp-uniform branches.
 template <int U>
 __device__ __forceinline__ bool sweep_step(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                           int sr0, int& s, int nsteps, uint32_t& ep, int& ro_next) {
+                                           int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
     if (s > 0) load_row(win[(kR - U) % kR], tile_cb + 4u * (uint32_t)ro_next);
     ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
-    int code;
-    do {
-        float w;
-        lds_entry(ep, w, code);
-        ep += 8;
-        // two-level test on the column bits instead of a switch: no jump table (constant-bank load + BRX) per tap
-        if (!(code & kEntryGap)) {
-            if (code & 2) {
-                if (code & 1) fma_tap<U, 3>(acc, win, w); else fma_tap<U, 2>(acc, win, w);
-            } else {
-                if (code & 1) fma_tap<U, 1>(acc, win, w); else fma_tap<U, 0>(acc, win, w);
-            }
-        }
-    } while (!(code & kEntryLast));
+    wp += 16;
+    wv[(U + 1) & 1] = lds_v4(wp);                                         // weights of step s + 1 (zero vector past the end)
+    const float4 w = wv[U & 1];
+#ifdef DIB_VOTE
+    if (__any_sync(0xffffffffu, w.x != 0.0f)) fma_tap<U, 0>(acc, win, w.x);
+    if (__any_sync(0xffffffffu, w.y != 0.0f)) fma_tap<U, 1>(acc, win, w.y);
+    if (__any_sync(0xffffffffu, w.z != 0.0f)) fma_tap<U, 2>(acc, win, w.z);
+    if (__any_sync(0xffffffffu, w.w != 0.0f)) fma_tap<U, 3>(acc, win, w.w);
+#else
+    if (w.x != 0.0f) fma_tap<U, 0>(acc, win, w.x);
+    if (w.y != 0.0f) fma_tap<U, 1>(acc, win, w.y);
+    if (w.z != 0.0f) fma_tap<U, 2>(acc, win, w.z);
+    if (w.w != 0.0f) fma_tap<U, 3>(acc, win, w.w);
+#endif
     ++s;
     return s < nsteps;
 }
@@ -359,10 +375,10 @@ __device__ __forceinline__ bool sweep_step(float (&acc)[kR][kCC], float (&win)[k
 template <int U>
 struct SweepRound {
     __device__ __forceinline__ static bool run(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                               int sr0, int& s, int nsteps, uint32_t& ep, int& ro_next) {
-        if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next)) return false;
+                                               int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
+        if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) return false;
         if constexpr (U + 1 < kR)
-            return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next);
+            return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv);
         else
             return true;
     }
@@ -376,21 +392,23 @@ __device__ __forceinline__ void compute_chunk(float (&acc)[kR][kCC], uint32_t st
     const uint32_t tile = rowtab + kRowTabBytes;
 #pragma unroll 1
     for (int sg = 0; sg < nseg; ++sg) {
-        int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, eoff} as two words
+        int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, woff} as two words
         lds_entry(aux + 8u * (uint32_t)sg, reinterpret_cast<float&>(raw0), raw1);
         const int seg_dx0 = (int)(short)(raw0 & 0xffff), seg_dy0 = raw0 >> 16;
-        const int nsteps = (int)(short)(raw1 & 0xffff), seg_eoff = raw1 >> 16;
+        const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
         const int colbase = wcol * (32 * kCC) + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
         const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
         const int sr0 = wrow * kR - seg_dy0 + dy_hi;      // staged row of output row 0 at step 0
-        uint32_t ep = aux + kChunkSegBytes + 8u * (uint32_t)seg_eoff;
+        uint32_t wp = aux + kChunkSegBytes + 16u * (uint32_t)seg_woff;
+        float4 wv[2];
+        wv[0] = lds_v4(wp);
         float win[kR][kWinW];
 #pragma unroll
         for (int r = 0; r < kR; ++r) load_row(win[r], tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + r)));
         int ro_next = 0;
         int s = 0;
 #pragma unroll 1
-        while (SweepRound<0>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, ep, ro_next)) {
+        while (SweepRound<0>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) {
         }
     }
 }
@@ -421,17 +439,19 @@ __device__ __noinline__ void store_row_epilogue(const float* srow, float* g, con
     }
 }
 
-// Aligned quad k of a staged row covers row elements x0 = 4k - skew .. x0 + 3: one 16-byte store when it lies
-// inside [0, wv), element-wise at the (at most two) quads that straddle an end of the row.
-__device__ __forceinline__ void store_quad(float* g, uint32_t srow, int k, int skew, int wv) {
-    const int x0 = 4 * k - skew;
-    if (x0 >= 0 && x0 + 3 < wv) {
-        *reinterpret_cast<float4*>(g + x0) = lds_v4(srow + 16u * (uint32_t)k);
-    } else if (x0 + 3 >= 0 && x0 < wv) {
+// One staged row -> global without epilogue.  Element x of the row sits at srow + 4 * (skew + x).  Aligned quads
+// k0 .. k1-1 lie wholly inside [0, wv) and go out as 16-byte stores; the <= 3 elements before the first and after the
+// last whole quad are stored one per lane.
+__device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int skew, int wv, int lane) {
+    const int k0 = (skew + 3) >> 2, k1 = (wv + skew) >> 2;
+    const int head = min(4 * k0 - skew, wv), tail0 = max(4 * k1 - skew, head);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (x0 + j >= 0 && x0 + j < wv) g[x0 + j] = lds_f32(srow + 16u * (uint32_t)k + 4u * j);
+    for (int it = 0; it < 2; ++it) {
+        const int k = lane + 32 * it;
+        if (k >= k0 && k < k1) *reinterpret_cast<float4*>(g + (4 * k - skew)) = lds_v4(srow + 16u * (uint32_t)k);
     }
+    const int x = lane < head ? lane : tail0 + (lane - head);
+    if (x < wv && (lane < head || x >= tail0)) g[x] = lds_f32(srow + 4u * (uint32_t)(skew + x));
 }
 
 template <bool kEpi>
@@ -467,14 +487,8 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
         __syncwarp();
         float* g1 = g + im.dst_rp;
         if (!kEpi) {
-            if (r < nrows) {
-                store_quad(g, b0, lane, skew0, wv);
-                store_quad(g, b0, lane + 32, skew0, wv);
-            }
-            if (r + 1 < nrows) {
-                store_quad(g1, b1, lane, skew1, wv);
-                store_quad(g1, b1, lane + 32, skew1, wv);
-            }
+            if (r < nrows) store_row_plain(g, b0, skew0, wv, lane);
+            if (r + 1 < nrows) store_row_plain(g1, b1, skew1, wv, lane);
         } else {
             const uint64_t stream = p.philox_offset + (uint64_t)im.philox_slot;
             const float* sm0 = reinterpret_cast<const float*>(__cvta_shared_to_generic(b0));
@@ -501,8 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
     uint64_t* full = bars;          // [2] producers -> consumers: stage loaded
     uint64_t* empty = bars + 2;     // [2] consumers -> producers: stage may be refilled
-    const int tile_begin = p.cta_begin[blockIdx.x], tile_end = p.cta_begin[blockIdx.x + 1];
-    if (tile_begin >= tile_end) return;
+    int* tile_slots = reinterpret_cast<int*>(bars + 4);
     const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
@@ -521,19 +534,31 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         // ------------------------------------------------ producer warpgroup
         const int pt = threadIdx.x - kComputeWarps * 32;
         Stage cur, nxt;
-        cur.tile = tile_begin;
+        int nfetch = 0;
+        cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
         cur.chunk = 0;
-        decode_tile(p, cur.tile, cur);
-        cur.rec = load_chunk_rec(p, cur.img, 0);
+        if (cur.tile >= 0) {
+            decode_tile(p, cur.tile, cur);
+            cur.rec = load_chunk_rec(p, cur.img, 0);
+        }
         for (int n = 0;; ++n) {
             const int b = n & 1;
-            next_stage(p, cur, tile_end, nxt);                        // its chunk record is in flight during the issue below
+            next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the issue below
             if (n >= 2) mbar_wait(&empty[b], ((n >> 1) - 1) & 1);    // consumers released the stage that used this buffer
             const StageSmem sm = stage_smem(smem, b);
             if (cur.tile < 0) {
                 if (pt == 0) sm.hdr->tile = -1;
                 mbar_arrive_expect_tx(&full[b], 0);
                 cp_async_mbar_arrive(&full[b]);
+                // this CTA has stopped fetching; the last CTA to get here rewinds the scheduler for the next launch
+                if (pt == 0) {
+                    __threadfence();
+                    if (atomicAdd(&p.sched->done_ctas, 1u) == gridDim.x - 1) {
+                        p.sched->next_tile = 0u;
+                        p.sched->done_ctas = 0u;
+                        __threadfence();
+                    }
+                }
                 break;
             }
             issue_stage(p, cur, sm, &full[b], pt);
@@ -583,7 +608,7 @@ int tiled_tile_counts(int H, int W, int* tiles_y, int* tiles_x) {
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 uint64_t seed, uint64_t offset, cudaStream_t st) {
+                 SchedWords* sched, uint64_t seed, uint64_t offset, cudaStream_t st) {
     static thread_local int sm_count = 0;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
@@ -596,9 +621,8 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     }
     TiledParams p;
     int total = 0;
-    double total_cost = 0.0;
-    double tile_cost[DIB_MAX_BATCH];
-    for (int k = 0; k < n_sel; ++k) {
+    bool any_epi = false;
+    for (int k = 0; k < n_sel; ++k) {   // `order` lists the images heaviest PSF first: tiles are handed out in this order
         const dib_image& im = images[order[k]];
         const dib_psf_meta& m = meta_host[im.psf_index];
         TiledImage& t = p.img[k];
@@ -618,6 +642,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.nchunks = m.prog_chunks;
         t.epilogue = im.epilogue;
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
+        any_epi |= (t.epilogue != 0);
         t.philox_slot = order[k];
         t.noise_sd = im.noise_sd;
         t.gamma = im.gamma;
@@ -626,35 +651,14 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
             t.std[c] = im.std[c];
         }
         total += per_ch * im.C;
-        // cost of one tile of this image in "tap equivalents": FMAs per pixel + window fills + staging/stores
-        tile_cost[k] = (double)m.count + 0.35 * (double)m.prog_steps + 4.0 * (double)m.prog_chunks + 8.0;
-        total_cost += tile_cost[k] * per_ch * im.C;
     }
     p.prog = prog;
     p.n_images = n_sel;
     p.total_tiles = total;
     p.philox_seed = seed;
     p.philox_offset = offset;
-    // cost-balanced contiguous partition of the tile list over the CTAs (one CTA per SM)
-    const int grid = total < sm_count ? total : (sm_count > 159 ? 159 : sm_count);
-    {
-        int b = 0;
-        double acc_cost = 0.0;
-        p.cta_begin[0] = 0;
-        int img = 0;
-        for (int tix = 0; tix < total; ++tix) {
-            while (img + 1 < n_sel && tix >= p.img[img + 1].first_tile) ++img;
-            const double target = total_cost * (double)(b + 1) / (double)grid;
-            acc_cost += tile_cost[img];
-            if (acc_cost >= target - 1e-9 && b + 1 < grid) {
-                ++b;
-                p.cta_begin[b] = tix + 1;
-            }
-        }
-        for (int k = b + 1; k <= grid; ++k) p.cta_begin[k] = total;
-    }
-    bool any_epi = false;
-    for (int k = 0; k < n_sel; ++k) any_epi |= (p.img[k].epilogue != 0);
+    p.sched = sched;
+    const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
     if (any_epi)
         blur_tiled_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
     else

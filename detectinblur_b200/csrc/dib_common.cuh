@@ -31,12 +31,11 @@ void set_error(const char* fmt, ...);
 
 // ---- tap set layout (see include/dib.h) ----
 // Tiled-kernel program of one PSF (built by taps.cu, executed by blur_tiled.cu).  The PSF support is cut into
-// groups of kGroupW columns; a SEGMENT is one group's run of rows [dy0, dy0 + nsteps).  The kernel sweeps a segment
-// row by row ("steps"); for every step the program lists the taps present as ENTRIES (weight, column-in-group), so
-// the kernel never tests for absent taps.  Segments are packed into CHUNKS whose tap extents are bounded
-// (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that tile + halo of any chunk fits the kernel's fixed
-// shared-memory stage, whatever the PSF's overall extent.
-constexpr int kGroupW = 4;              // PSF columns per group
+// groups of kGroupW columns; a SEGMENT is one group's run of rows [dy0, dy0 + nsteps) with one kGroupW-wide weight
+// vector per row ("step"; zero where the PSF has no tap -- the kernel skips those with uniform branches).  Segments
+// are packed into CHUNKS whose tap extents are bounded (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that
+// tile + halo of any chunk fits the kernel's fixed shared-memory stage, whatever the PSF's overall extent.
+constexpr int kGroupW = 4;              // PSF columns per group (one float4 of weights per step)
 constexpr int kChunkGroups = 5;         // groups per chunk  -> column halo <= 19
 constexpr int kChunkHaloRows = 17;      // dy_hi - dy_lo per chunk
 constexpr int kProgMaxChunks = 32;
@@ -44,28 +43,28 @@ struct SegRec {         // 8 bytes
     int16_t dx0;        // first tap column of the group, relative to the PSF centre (tap dx = x - centre)
     int16_t dy0;        // first tap row of the run, relative to the centre
     int16_t nsteps;     // rows in the run
-    int16_t eoff;       // index of the run's first entry inside the chunk's entry array
+    int16_t woff;       // index of the run's first weight vector inside the chunk's weight array
 };
-struct TapEntry {       // 8 bytes
-    float w;            // normalised tap weight
-    int32_t code;       // bits 0-2: column inside the group (0..3) or kEntryGap; bit 3: last entry of its step
-};
-constexpr int kEntryGap = 4;            // a step without taps (a hole inside the run): nothing to accumulate
-constexpr int kEntryLast = 8;
 struct ChunkRec {       // 16 bytes
     int16_t dy_lo, dy_hi;   // tap row range of the chunk (relative to the centre)
     int16_t dx_lo, dx_hi;   // tap column range: first group's dx0 .. last group's dx0 + kGroupW - 1
     int16_t nseg;           // segments in the chunk (<= kChunkGroups)
-    int16_t nentries;       // entries in the chunk
+    int16_t wsteps;         // weight vectors in the chunk
     int32_t data_off;       // byte offset of the chunk's data block inside the PSF's program section
 };
-// chunk data block: SegRec slots (48 B, fixed) then TapEntry[nentries]
+// chunk data block: SegRec slots (48 B, fixed) then float4[wsteps] (+ one zero vector: the kernel prefetches one ahead)
 constexpr int kChunkSegBytes = 48;
-constexpr int kChunkMaxEntries = kChunkGroups * kGroupW * (kChunkHaloRows + 1);          // 420
-constexpr int kChunkDataMax = kChunkSegBytes + 8 * kChunkMaxEntries;                      // 3408
+constexpr int kChunkMaxSteps = kChunkGroups * (kChunkHaloRows + 1);                       // 90
+constexpr int kChunkDataMax = kChunkSegBytes + 16 * (kChunkMaxSteps + 1);                 // 1504
 constexpr size_t kProgHeaderBytes = sizeof(ChunkRec) * kProgMaxChunks;                    // 512
 constexpr size_t kProgDataBytes = 16384;
 constexpr size_t kProgBytes = kProgHeaderBytes + kProgDataBytes;
+
+// Work-distribution words of the tiled kernel (self-resetting, see blur_tiled.cu)
+struct SchedWords {
+    unsigned int next_tile;     // next tile to hand out
+    unsigned int done_ctas;     // CTAs that have stopped fetching
+};
 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
@@ -75,7 +74,8 @@ inline dib_tapset_layout tapset_layout(int n, int max_taps) {
     L.taps_offset = align256(sizeof(dib_psf_meta) * (size_t)n);
     L.prog_offset = L.taps_offset + align256(sizeof(dib_tap) * (size_t)n * (size_t)max_taps);
     L.prog_bytes_per_psf = kProgBytes;
-    L.total_bytes = L.prog_offset + kProgBytes * (size_t)n;
+    L.sched_offset = L.prog_offset + kProgBytes * (size_t)n;
+    L.total_bytes = L.sched_offset + 256;
     return L;
 }
 

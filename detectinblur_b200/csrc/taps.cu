@@ -75,7 +75,7 @@ __device__ inline int block_min_int(int v, int* sh) {
 template <typename T>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
-                    dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog) {
+                    dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog, SchedWords* __restrict__ sched) {
     __shared__ double sh_d[kCompactThreads / 32];
     __shared__ long long sh_ll[kCompactThreads / 32];
     __shared__ int sh_i[kCompactThreads / 32];
@@ -84,10 +84,13 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ unsigned sh_occ[32 * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
     __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
-    __shared__ int sh_segcount[kProgMaxChunks * kChunkGroups];
     __shared__ int sh_nchunks, sh_nsegs, sh_total_steps;
 
     const int n = blockIdx.x;
+    if (n == 0 && threadIdx.x == 0) {
+        sched->next_tile = 0u;
+        sched->done_ctas = 0u;
+    }
     const T* psf = psfs + (int64_t)n * psf_stride;
     const int cells = side * side;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -220,7 +223,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                         sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
                         sg.dy0 = (int16_t)(f - centre);
                         sg.nsteps = (int16_t)(l - f + 1);
-                        sg.eoff = 0;
+                        sg.woff = 0;
                         lo = min(lo, f - centre);
                         hi = max(hi, l - centre);
                         xlo = min(xlo, (int)sg.dx0);
@@ -231,7 +234,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                     }
                     c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
                     c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
-                    c.nseg = (int16_t)nseg; c.nentries = 0;
+                    c.nseg = (int16_t)nseg; c.wsteps = 0;
                     c.data_off = 0;
                     sh_chunks[nchunks] = c;
                     ++nchunks;
@@ -243,44 +246,23 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         }
         __syncthreads();
         int nchunks = sh_nchunks;
-        // 3c. one thread per segment counts its entries: per step the taps present, or one gap entry
+        // 3c. offsets: weight vectors of a chunk's segments are laid out back to back
         if (nchunks > 0) {
-            for (int k = tid; k < nchunks * kChunkGroups; k += kCompactThreads) {
-                const int ci = k / kChunkGroups, sgi = k % kChunkGroups;
-                int cnt = 0;
-                if (sgi < sh_chunks[ci].nseg) {
-                    const SegRec sg = sh_segs[k];
-                    for (int st = 0; st < sg.nsteps; ++st) {
-                        int nz = 0;
-                        for (int e = 0; e < kGroupW; ++e) {
-                            const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + st;
-                            if (x < side) {
-                                const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
-                                const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
-                                nz += (w != 0.0f);
-                            }
-                        }
-                        cnt += nz ? nz : 1;
-                    }
-                }
-                sh_segcount[k] = cnt;
-            }
-            __syncthreads();
             if (tid == 0) {
                 int data_off = (int)kProgHeaderBytes, total_steps = 0;
                 bool ok = true;
                 for (int ci = 0; ci < nchunks && ok; ++ci) {
-                    int ne = 0;
+                    int nw = 0;
                     for (int sgi = 0; sgi < sh_chunks[ci].nseg; ++sgi) {
-                        sh_segs[ci * kChunkGroups + sgi].eoff = (int16_t)ne;
-                        ne += sh_segcount[ci * kChunkGroups + sgi];
-                        total_steps += sh_segs[ci * kChunkGroups + sgi].nsteps;
+                        sh_segs[ci * kChunkGroups + sgi].woff = (int16_t)nw;
+                        nw += sh_segs[ci * kChunkGroups + sgi].nsteps;
                     }
-                    const int bytes = kChunkSegBytes + 8 * ne;
-                    if (ne > kChunkMaxEntries || data_off + bytes > (int)kProgBytes) { ok = false; break; }
-                    sh_chunks[ci].nentries = (int16_t)ne;
+                    total_steps += nw;
+                    const int bytes = kChunkSegBytes + 16 * (nw + 1);
+                    if (nw > kChunkMaxSteps || data_off + bytes > (int)kProgBytes) { ok = false; break; }
+                    sh_chunks[ci].wsteps = (int16_t)nw;
                     sh_chunks[ci].data_off = data_off;
-                    data_off += (bytes + 15) & ~15;
+                    data_off += bytes;
                 }
                 if (!ok) sh_nchunks = -1;
                 sh_total_steps = total_steps;
@@ -288,42 +270,32 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             __syncthreads();
             nchunks = sh_nchunks;
         }
-        // 3d. write chunk records, segment records and entries
+        // 3d. write chunk records, segment records and weight vectors
         if (nchunks > 0) {
             for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
-            for (int k = tid; k < nchunks * kChunkGroups; k += kCompactThreads) {
-                const int ci = k / kChunkGroups, sgi = k % kChunkGroups;
+            for (int ci = 0; ci < nchunks; ++ci) {
                 const ChunkRec c = sh_chunks[ci];
                 SegRec* seg_out = reinterpret_cast<SegRec*>(my_prog + c.data_off);
-                SegRec sg;
-                sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.eoff = 0;
-                if (sgi < c.nseg) sg = sh_segs[k];
-                seg_out[sgi] = sg;
-                if (sgi >= c.nseg) continue;
-                TapEntry* ent = reinterpret_cast<TapEntry*>(my_prog + c.data_off + kChunkSegBytes) + sg.eoff;
-                int pos = 0;
-                for (int st = 0; st < sg.nsteps; ++st) {
-                    int first = pos;
-                    for (int e = 0; e < kGroupW; ++e) {
-                        const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + st;
+                float* wout = reinterpret_cast<float*>(my_prog + c.data_off + kChunkSegBytes);
+                if (tid < kChunkSegBytes / (int)sizeof(SegRec)) {
+                    SegRec sg;
+                    sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.woff = 0;
+                    if (tid < c.nseg) sg = sh_segs[ci * kChunkGroups + tid];
+                    seg_out[tid] = sg;
+                }
+                if (tid < kGroupW) wout[c.wsteps * kGroupW + tid] = 0.0f;     // the vector the kernel prefetches past the end
+                for (int sgi = 0; sgi < c.nseg; ++sgi) {
+                    const SegRec sg = sh_segs[ci * kChunkGroups + sgi];
+                    for (int k = tid; k < sg.nsteps * kGroupW; k += kCompactThreads) {
+                        const int step = k / kGroupW, e = k % kGroupW;
+                        const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
+                        float w = 0.0f;
                         if (x < side) {
                             const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
-                            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
-                            if (w != 0.0f) {
-                                TapEntry t;
-                                t.w = w;
-                                t.code = e;
-                                ent[pos++] = t;
-                            }
+                            w = normalize ? PsfNum<T>::normalized(v, s) : v;
                         }
+                        wout[(sg.woff + step) * kGroupW + e] = w;
                     }
-                    if (pos == first) {
-                        TapEntry t;
-                        t.w = 0.0f;
-                        t.code = kEntryGap;
-                        ent[pos++] = t;
-                    }
-                    ent[pos - 1].code |= kEntryLast;
                 }
             }
         }
@@ -346,6 +318,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         m.prog_chunks = nchunks_final;
         m.prog_steps = nchunks_final ? sh_total_steps : 0;
         m.flags = flags;
+        m.prog_segs = nchunks_final ? sh_nsegs : 0;
+        m.reserved = 0;
         m.sy = (double)sy;
         m.sx = (double)sx;
         m.syy = (double)syy;
@@ -372,13 +346,14 @@ extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int
     dib_psf_meta* meta = reinterpret_cast<dib_psf_meta*>(base + L.meta_offset);
     dib_tap* taps = reinterpret_cast<dib_tap*>(base + L.taps_offset);
     uint8_t* prog = base + L.prog_offset;
+    SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (psf_dtype == DIB_F32) {
         compact_taps_kernel<float><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const float*>(psfs), side, psf_stride,
-                                                                       normalize, meta, taps, max_taps, prog);
+                                                                       normalize, meta, taps, max_taps, prog, sched);
     } else {
         compact_taps_kernel<__half><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const __half*>(psfs), side, psf_stride,
-                                                                        normalize, meta, taps, max_taps, prog);
+                                                                        normalize, meta, taps, max_taps, prog, sched);
     }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;

@@ -67,6 +67,8 @@ typedef struct dib_psf_meta {
     int32_t prog_chunks;      /* chunks of the tiled-kernel program (0: none was built) */
     int32_t prog_steps;       /* total weight vectors (window steps) of that program */
     int32_t flags;            /* DIB_META_* */
+    int32_t prog_segs;        /* segments (column-group runs) of that program */
+    int32_t reserved;
     double sy, sx;            /* sums over the support of y, x         (transforms.py:367-371) */
     double syy, sxx, sxy;     /* sums of y*y, x*x, y*x over the support (transforms.py:373-376) */
 } dib_psf_meta;
@@ -80,9 +82,11 @@ typedef struct dib_psf_meta {
  *   meta   : dib_psf_meta[n]
  *   taps   : dib_tap[n][max_taps]
  *   prog   : uint8[n][prog_bytes]     program of the tiled kernel (opaque)
+ *   sched  : 256 bytes                work-distribution words of the tiled kernel (zeroed by dib_compact_taps, left
+ *                                     zero by every dib_blur_batch; one blur call per tap set may be in flight at a time)
  */
 typedef struct dib_tapset_layout {
-    size_t meta_offset, taps_offset, prog_offset, prog_bytes_per_psf, total_bytes;
+    size_t meta_offset, taps_offset, prog_offset, prog_bytes_per_psf, sched_offset, total_bytes;
 } dib_tapset_layout;
 
 /* One image of a blur batch (a CHW plane stack anywhere in device memory). */
@@ -144,7 +148,7 @@ DIB_API int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int si
  *   philox_seed / philox_offset   counter-based RNG stream for DIB_EPI_PHILOX
  *   launches    if not NULL, receives the number of kernels launched
  */
-DIB_API int dib_blur_batch(const dib_image* images, int n_images, const void* tapset, int n_psfs, int max_taps,
+DIB_API int dib_blur_batch(const dib_image* images, int n_images, void* tapset, int n_psfs, int max_taps,
                    const dib_psf_meta* meta_host, int io_dtype, int algo, uint64_t philox_seed,
                    uint64_t philox_offset, int* launches, void* stream);
 
