@@ -40,7 +40,6 @@ class Trajectory(object):
         if expl > 0:
             v = v0 * expl
         x = np.zeros(iters, dtype=np.complex128)
-        pos = complex(0.0, 0.0)
         tot_length = 0
         big = 0
         shake_threshold = prob_big_shake * expl
@@ -53,13 +52,13 @@ class Trajectory(object):
             else:
                 kick = 0
             g = complex(rnd.randn(), rnd.randn())
-            dv = kick + expl * (gaussian_shake * g - centripetal * pos) * step
+            # x[t] is a numpy complex128 scalar, which makes dv and v numpy scalars too: numpy divides a complex by
+            # multiplying with the reciprocal, CPython by dividing, and the reference's bits come from the former
+            dv = kick + expl * (gaussian_shake * g - centripetal * x[t]) * step
             v += dv
             v = (v / float(np.abs(v))) * norm_len
-            nxt = pos + v
-            x[t + 1] = nxt
-            tot_length = tot_length + abs(nxt - pos)
-            pos = nxt
+            x[t + 1] = x[t] + v
+            tot_length = tot_length + abs(x[t + 1] - x[t])
         self.unprocessedX = np.copy(x)
         self.x = x + complex(self.canvas / 2, self.canvas / 2)      # start point at the canvas centre (:92)
         self.tot_length = tot_length

@@ -1,0 +1,153 @@
+"""GPU tests of the host-side mirrors that sit either side of the blur kernel: BlurImage with the CUDA rasteriser,
+deferred PSFs completed in the main process, the PSF class, and the fused blur -> normalize -> padded batch."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+from oracle import blur_oracle as bo  # noqa: E402
+from oracle import psf_oracle as po  # noqa: E402
+from tests.test_transforms_cpu import CONFIGS  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda")
+
+
+def _golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "transform_cases.npz"), allow_pickle=False)
+
+
+def test_blur_image_on_the_fly_cuda_backend_matches_reference(cuda, golden_dir):
+    from detectinblur_b200.transforms import BlurImage, complete_blur_dicts
+    g = _golden(golden_dir)
+    img = Image.fromarray(np.random.default_rng(3).integers(0, 256, (96, 112, 3), dtype=np.uint8))
+    checked = 0
+    for n in range(int(g["n"])):
+        ci, seed = (int(v) for v in g["cfg_%d" % n])
+        kw = dict(CONFIGS[ci])
+        if kw.get("use_stored_psfs") or not bool(g["blurring_%d" % n]):
+            continue
+        kw.setdefault("blur_image_in_transform", False)
+        shape = tuple(int(v) for v in g["psf_shape_%d" % n])
+        ref = np.zeros(int(np.prod(shape)))
+        ref[g["psf_idx_%d" % n]] = g["psf_val_%d" % n]
+        ref = ref.reshape(shape)
+        for backend in ("cuda", "defer"):
+            random.seed(seed)
+            np.random.seed(seed)
+            _, _, bd = BlurImage(psf_backend=backend, **kw)(img, None, {})
+            if backend == "defer":
+                assert bd["psf"] is None
+                psfs = complete_blur_dicts([bd], cuda, dtype=torch.float16)
+                assert psfs[0].dtype == torch.float16 and tuple(psfs[0].shape) == shape
+                assert np.array_equal(psfs[0].cpu().numpy(), ref.astype(np.float16))
+            assert bd["psf"].dtype == np.float64 and np.array_equal(bd["psf"], ref), (n, backend)
+            theta, s1, s2 = g["scalars_%d" % n]
+            assert bd["theta_rad"] == theta and bd["scale_factor_lambda1"] == s1 and bd["scale_factor_lambda2"] == s2
+            assert random.random() == float(g["next_random_%d" % n])
+        checked += 1
+    assert checked >= 10
+
+
+def test_psf_class_mirror(cuda, golden_dir):
+    from detectinblur_b200.motion_blur import PSF, Trajectory
+    g = np.load(os.path.join(golden_dir, "psf_cases.npz"), allow_pickle=False)
+    for k in (0, 3, 8):
+        expl, frac, seed = g["meta_%d" % k]
+        np.random.seed(int(seed))
+        tr = Trajectory(canvas=256, max_len=96, expl=expl).fit().fit()
+        ps = PSF(canvas=256, trajectory=tr, fraction=[frac])
+        out = ps.fit()
+        raw = np.zeros(256 * 256)
+        raw[g["raw_idx_%d" % k]] = g["raw_val_%d" % k]
+        assert out is ps.PSFs and np.array_equal(ps.PSFs[0].ravel(), raw)
+        ps.centerPSF()
+        cen = np.zeros(256 * 256)
+        cen[g["cen_idx_%d" % k]] = g["cen_val_%d" % k]
+        assert np.array_equal(ps.PSFs[0].ravel(), cen)
+        left, top, right, bottom = ps.findOffsets()
+        ys, xs = np.nonzero(cen.reshape(256, 256))
+        assert right == max(0, xs.max() - 127) and left == max(0, 127 - xs.min())
+        assert bottom == max(0, ys.max() - 127) and top == max(0, 127 - ys.min())
+
+
+def test_cpu_blur_flag_blurs_on_the_gpu(cuda):
+    """blur_image_in_transform=True (--cpu_blur) returns a blurred uint8 PIL image produced by the CUDA kernel."""
+    from detectinblur_b200.transforms import BlurImage
+    arr = np.random.default_rng(1).integers(0, 256, (90, 120, 3), dtype=np.uint8)
+    img = Image.fromarray(arr)
+    random.seed(11)
+    np.random.seed(11)
+    out, _, bd = BlurImage(prob=1.0, blur_type=0.005, blur_exposure=1 / 5, blur_image_in_transform=True, psf_backend="cuda")(img, None, {})
+    assert out.size == img.size and out.mode == "RGB"
+    psfn = bo.normalize_psf(bd["psf"].astype(np.float32))
+    want = bo.manual_blur(arr.transpose(2, 0, 1).astype(np.float32) / np.float32(255), psfn)
+    got = np.asarray(out).transpose(2, 0, 1).astype(np.float64) / 255
+    assert np.abs(got - np.clip(want, 0, 1)).max() <= 1.0 / 255 + 1e-6
+
+
+def test_fused_blur_normalize_batch(cuda):
+    from detectinblur_b200 import net_transforms as nt
+    rng = np.random.default_rng(8)
+    shapes = [(3, 97, 131), (3, 120, 100), (3, 70, 140)]
+    imgs = [rng.random(s, dtype=np.float32) for s in shapes]
+    np.random.seed(8)
+    psfs = []
+    for frac in (1 / 10, 1 / 5, 1 / 18):
+        p16, _ = po.stored_psf(0.005, frac, np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    blur_dicts = [{"blurring": True}, {"blurring": False}, {"blurring": True}]
+    means = np.array([[0.47, 0.45, 0.41], nt.CANONICAL_MEAN, [0.5, 0.4, 0.3]])
+    stds = np.array([[0.21, 0.2, 0.22], nt.CANONICAL_STD, [0.25, 0.2, 0.3]])
+    for exact in (True, False):
+        il = nt.fused_blur_normalize([torch.from_numpy(a).to(cuda) for a in imgs], blur_dicts,
+                                     [torch.from_numpy(p).to(cuda) for p in psfs], newMeans=means, newSTDs=stds, exact=exact)
+        assert tuple(il.tensors.shape) == (3, 3, 128, 160) and il.image_sizes == [(97, 131), (120, 100), (70, 140)]
+        for k, (a, bd) in enumerate(zip(imgs, blur_dicts)):
+            base = bo.manual_blur(a, bo.normalize_psf(psfs[k])) if bd["blurring"] else a
+            want = bo.normalize_image(base, means[k], stds[k])
+            got = il.tensors[k, :, :a.shape[1], :a.shape[2]].cpu().numpy()
+            if exact:
+                assert np.array_equal(got, want), k
+            else:
+                assert np.abs(got - want).max() <= 1e-4, k
+            assert il.tensors[k, :, a.shape[1]:, :].abs().max().item() == 0
+            assert il.tensors[k, :, :, a.shape[2]:].abs().max().item() == 0
+    # the reference-shaped module accepts the fused result unchanged
+    tr = nt.GeneralizedRCNNTransform(800, 1333, nt.CANONICAL_MEAN, nt.CANONICAL_STD, normalize_images=False)
+    out, _ = tr(il)
+    assert out is il
+    # and its own normalize + batch path agrees with the oracle's normalize on an unblurred list
+    tr2 = nt.GeneralizedRCNNTransform(97, 131, nt.CANONICAL_MEAN, nt.CANONICAL_STD)
+    one, _ = tr2([torch.from_numpy(imgs[0]).to(cuda)])
+    assert np.array_equal(one.tensors[0, :, :97, :131].cpu().numpy(), bo.normalize_image(imgs[0], nt.CANONICAL_MEAN, nt.CANONICAL_STD))
+
+
+def test_philox_noise_statistics(cuda):
+    """In-kernel Philox noise (fast mode): clamp range, mean and variance of the injected noise."""
+    import math
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+    img = torch.full((3, 200, 300), 0.5, device=cuda)
+    delta = torch.zeros(1, 128, 128, device=cuda)
+    delta[0, 63, 63] = 1
+    ts = ops.compact_taps(delta, normalize=False)
+    sd = math.sqrt(0.004)
+    for exact in (True, False):
+        out = bf.blur_batch([img], ts, [0], noise_sd=[sd], philox_seed=1234, exact=exact)[0]
+        assert out.min().item() >= 0 and out.max().item() <= 1
+        d = (out - 0.5).double()
+        assert abs(d.mean().item()) < 5e-4 and abs(d.std().item() - sd) < 1e-3
+        again = bf.blur_batch([img], ts, [0], noise_sd=[sd], philox_seed=1234, exact=exact)[0]
+        assert torch.equal(out, again)          # counter-based: same seed, same noise
+        other = bf.blur_batch([img], ts, [0], noise_sd=[sd], philox_seed=99, exact=exact)[0]
+        assert not torch.equal(out, other)

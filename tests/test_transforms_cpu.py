@@ -1,0 +1,98 @@
+"""CPU checks of the BlurImage mirror against the golden blur_dicts made by the unmodified reference: python `random`
+consumption, stored-PSF loading, not-blurring defaults, and (through the oracle rasteriser) deferred on-the-fly PSFs."""
+import os
+import random
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import psf_oracle as po
+
+CONFIGS = [
+    dict(prob=0.9, use_stored_psfs=False, low_exposure=False, high_exposure=False),
+    dict(prob=0.75, blur_type=0.005, use_stored_psfs=False, low_exposure=True),
+    dict(prob=1.0, blur_type=0.00005, use_stored_psfs=False, high_exposure=True),
+    dict(prob=1.0, blur_type=0.001, blur_exposure=1 / 25, use_stored_psfs=False),
+    dict(prob=0.75, blur_type=1, use_stored_psfs=True, low_exposure=True),
+    dict(prob=1.0, blur_type=3, use_stored_psfs=True, high_exposure=True),
+    dict(prob=0.9, use_stored_psfs=True),
+    dict(prob=1.0, use_stored_psfs=False, dont_center_psf=True, blur_type=0.001, low_exposure=True),
+    dict(prob=0.0),
+]   # must stay in step with tools/make_golden.py:gen_transform_cases
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "transform_cases.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="module")
+def bank(golden, tmp_path_factory):
+    root = tmp_path_factory.mktemp("bank")
+    for i, name in enumerate(golden["bank_names"]):
+        psf = np.zeros(256 * 256, np.float16)
+        psf[golden["bank_idx_%d" % i]] = golden["bank_val_%d" % i]
+        path = os.path.join(str(root), str(name))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            np.save(f, psf.reshape(256, 256))
+    return str(root)
+
+
+def test_blur_image_mirror_matches_reference(golden, bank):
+    from detectinblur_b200.transforms import BlurImage
+    img = Image.fromarray(np.random.default_rng(3).integers(0, 256, (96, 112, 3), dtype=np.uint8))
+    for n in range(int(golden["n"])):
+        ci, seed = (int(v) for v in golden["cfg_%d" % n])
+        kw = dict(CONFIGS[ci])
+        kw.setdefault("blur_image_in_transform", False)
+        if kw.get("use_stored_psfs"):
+            kw["stored_psf_directory"] = bank
+        random.seed(seed)
+        np.random.seed(seed)
+        out_img, _, bd = BlurImage(psf_backend="defer", **kw)(img, None, {})
+        assert out_img is img
+        assert bool(bd["blurring"]) == bool(golden["blurring_%d" % n]), n
+        # python's RNG must have been consumed exactly as the reference consumed it
+        assert random.random() == float(golden["next_random_%d" % n]), "case %d: random stream out of step" % n
+        want_idx = [None if v == -99 else int(v) for v in golden["indices_%d" % n]]
+        got_idx = [None if bd[k] is None else int(bd[k]) for k in ("param_index", "fraction_index")]
+        assert got_idx == want_idx, n
+        if not bd["blurring"]:
+            assert bd["psf"] == [0] and bd["theta_rad"] == 0 and bd["scale_factor_lambda1"] == 1
+            continue
+        shape = tuple(int(v) for v in golden["psf_shape_%d" % n])
+        ref = np.zeros(int(np.prod(shape)), dtype=np.dtype(str(golden["psf_dtype_%d" % n])))
+        ref[golden["psf_idx_%d" % n]] = golden["psf_val_%d" % n]
+        ref = ref.reshape(shape)
+        if bd["psf"] is None:
+            # deferred on-the-fly PSF: the mirror drew the trajectory; rasterise it with the oracle and compare
+            d = bd["deferred_psf"]
+            psf = po.rasterize(d["trajectory"], d["fraction"], 256)
+            if d["center"]:
+                psf = po.crop128(po.center(psf, 256))
+            assert psf.shape == shape
+            assert np.array_equal(psf, ref), n
+        else:
+            assert bd["psf"].dtype == ref.dtype and np.array_equal(bd["psf"], ref), n
+            theta, s1, s2 = golden["scalars_%d" % n]
+            assert bd["theta_rad"] == theta and bd["scale_factor_lambda1"] == s1 and bd["scale_factor_lambda2"] == s2
+
+
+def test_preblurred_passthrough():
+    from detectinblur_b200.transforms import BlurImage
+    img = Image.new("RGB", (80, 70))
+    out, tgt, bd = BlurImage(prob=1.0, blur_image_in_transform=False, psf_backend="defer")(img, "t", {"preBlurred": True})
+    assert out is img and tgt == "t" and bd["blurring"] is False and bd["psf"] == [0] and bd["inverseWarp"] is None
+
+
+def test_trajectory_mirror_bit_exact(golden_dir):
+    from detectinblur_b200.motion_blur.generate_trajectory import Trajectory
+    g = np.load(os.path.join(golden_dir, "psf_cases.npz"), allow_pickle=False)
+    for k in range(int(g["n"])):
+        expl, frac, seed = g["meta_%d" % k]
+        np.random.seed(int(seed))
+        tr = Trajectory(canvas=256, max_len=96, expl=expl).fit().fit()
+        assert np.array_equal(tr.x, g["x_%d" % k]), k
+        assert tr.x.dtype == np.complex128 and len(tr.x) == 2000
