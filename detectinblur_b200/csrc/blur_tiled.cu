@@ -3,7 +3,7 @@
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
 // persistent, warp-specialised launch per batch:
-//   * work unit  = one 36 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
+//   * work unit  = one 32 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
 //                  global ticket counter, images with the heaviest PSFs first;
 //   * producer   = one warp.  For every stage (tile x program chunk) it stages tile + halo global -> shared:
 //                  TMA bulk copies (cp.async.bulk, one per tile row, the 16-byte-aligned interior of the row
@@ -28,22 +28,24 @@
 
 namespace dib {
 
-// Shape of the register tiling.  The unrolled sweep body is kR (rotations) x kGroupW (tap columns) x kR * kCC FMAs of
-// 16 bytes each, and it has to stay resident in the instruction cache: kR = 6 gives 16 KB, kR = 8 gave 29 KB and
-// spent as many cycles waiting for instruction fetch as issuing (profiles/round1_notes.md).
+// Shape of the register tiling.  Every thread owns two kR x kCC output blocks that sit kBlockStride columns apart in the
+// same rows; the pair shares weights, control flow and addressing, and every multiply-add is a packed FFMA2
+// (fma.rn.f32x2: one issue slot, two FMAs -- measured 62 TFLOP/s at 8 warps/SM where 3-register FFMA reaches 50), which
+// leaves the other issue slots to the window loads and the sweep control.  The unrolled sweep body is
+// kR (rotations) x kGroupW (tap columns) x kR * kCC FFMA2 of 16 bytes = 7 KB: it has to stay in the instruction cache
+// (a 29 KB body stalled on instruction fetch as often as it issued, profiles/round1_notes.md).
 #ifndef DIB_R
-#define DIB_R 6
+#define DIB_R 4
 #endif
 #ifndef DIB_WARP_ROWS
-#define DIB_WARP_ROWS 6
-#endif
-#ifndef DIB_WARP_COLS
-#define DIB_WARP_COLS 2
+#define DIB_WARP_ROWS 8
 #endif
 constexpr int kR = DIB_R;                   // output rows per thread (= rotation period of the register window)
-constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
-constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps are arranged kWarpRows x kWarpCols over the tile
-constexpr int kWarpCols = DIB_WARP_COLS;
+constexpr int kCC = 7;                      // output columns per block (odd: conflict-free lane stride)
+constexpr int kBlockStride = 32 * kCC;      // 224: column distance of a thread's two blocks
+constexpr int kWarpW = 2 * kBlockStride;    // 448 output columns per warp
+constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps stack vertically over the tile
+constexpr int kWarpCols = 1;
 constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: equal load on the 4 SM sub-partitions
 constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
@@ -53,11 +55,11 @@ constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (k
                                  : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
 static_assert(kComputeWarps % 4 == 0 && kR % 2 == 0, "warpgroup-aligned compute warps, rows stored in pairs");
 constexpr int kTH = kWarpRows * kR;         // 32 output rows per tile
-constexpr int kTW = kWarpCols * 32 * kCC;   // 448 output columns per tile
+constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
 constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
 constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
 constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 3) + 3) / 4 * 4;   // 472 floats (16 B multiple)
-constexpr int kOutPitch = 32 * kCC + 4;     // one staged output row of a warp (skew <= 3)
+constexpr int kOutPitch = kWarpW + 4;       // one staged output row of a warp (skew <= 3)
 constexpr int kHdrBytes = 64;
 constexpr int kAuxBytes = (kChunkDataMax + 15) / 16 * 16;          // segment records + weights of one chunk
 constexpr int kRowTabBytes = ((kRowsMax * 4) + 15) / 16 * 16;
@@ -327,46 +329,54 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
 }
 
 // ---------------------------------------------------------------- compute
+// Packed pair of fp32 values: .x belongs to the thread's left block, .y to the block kBlockStride columns to the right.
+__device__ __forceinline__ float2 ffma2(float w, float2 x, float2 a) {
+    unsigned long long d, ww, xx, aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(ww), "l"(xx), "l"(aa));     // SASS: FFMA2 with a scalar weight operand
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(d));
+    return r;
+}
+
 // One tap of a sweep step: weight w multiplies the window shifted by E columns.  Logical window row r sits in
 // register slot (r - U) mod kR.  Row 0 -- the row loaded at the start of this step -- is consumed last, so the FMAs
 // on the older rows cover that load's latency.
 template <int U, int E>
-__device__ __forceinline__ void fma_tap(float (&acc)[kR][kCC], const float (&win)[kR][kWinW], const float w) {
+__device__ __forceinline__ void fma_tap(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kWinW], const float w) {
 #pragma unroll
     for (int rr = 1; rr <= kR; ++rr) {
         const int r = rr % kR;
 #pragma unroll
-        for (int c = 0; c < kCC; ++c) acc[r][c] = fmaf(w, win[(r - U + kR) % kR][c - E + kGroupW - 1], acc[r][c]);
+        for (int c = 0; c < kCC; ++c) acc[r][c] = ffma2(w, win[(r - U + kR) % kR][c - E + kGroupW - 1], acc[r][c]);
     }
 }
 
-__device__ __forceinline__ void load_row(float (&dst)[kWinW], uint32_t addr) {
+__device__ __forceinline__ void load_row(float2 (&dst)[kWinW], uint32_t addr) {
 #pragma unroll
-    for (int k = 0; k < kWinW; ++k) dst[k] = lds_f32(addr + 4 * k);
+    for (int k = 0; k < kWinW; ++k) {
+        dst[k].x = lds_f32(addr + 4 * k);
+        dst[k].y = lds_f32(addr + 4 * (k + kBlockStride));
+    }
 }
 
 // Step s of a segment sweep, s mod kR == U: fetch the new top row into the slot the previous step freed and the
 // NEXT step's weight vector (kR is even, so the two weight registers simply alternate), then accumulate the taps
 // present in this step's vector; absent taps are skipped with warp-uniform branches.
 template <int U>
-__device__ __forceinline__ bool sweep_step(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
+__device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
                                            int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
     if (s > 0) load_row(win[(kR - U) % kR], tile_cb + 4u * (uint32_t)ro_next);
     ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
     wp += 16;
     wv[(U + 1) & 1] = lds_v4(wp);                                         // weights of step s + 1 (zero vector past the end)
     const float4 w = wv[U & 1];
-#ifdef DIB_VOTE
-    if (__any_sync(0xffffffffu, w.x != 0.0f)) fma_tap<U, 0>(acc, win, w.x);
-    if (__any_sync(0xffffffffu, w.y != 0.0f)) fma_tap<U, 1>(acc, win, w.y);
-    if (__any_sync(0xffffffffu, w.z != 0.0f)) fma_tap<U, 2>(acc, win, w.z);
-    if (__any_sync(0xffffffffu, w.w != 0.0f)) fma_tap<U, 3>(acc, win, w.w);
-#else
     if (w.x != 0.0f) fma_tap<U, 0>(acc, win, w.x);
     if (w.y != 0.0f) fma_tap<U, 1>(acc, win, w.y);
     if (w.z != 0.0f) fma_tap<U, 2>(acc, win, w.z);
     if (w.w != 0.0f) fma_tap<U, 3>(acc, win, w.w);
-#endif
     ++s;
     return s < nsteps;
 }
@@ -374,7 +384,7 @@ __device__ __forceinline__ bool sweep_step(float (&acc)[kR][kCC], float (&win)[k
 // kR consecutive steps = one full rotation of the window registers
 template <int U>
 struct SweepRound {
-    __device__ __forceinline__ static bool run(float (&acc)[kR][kCC], float (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
+    __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
                                                int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
         if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) return false;
         if constexpr (U + 1 < kR)
@@ -384,25 +394,29 @@ struct SweepRound {
     }
 };
 
-__device__ __forceinline__ void compute_chunk(float (&acc)[kR][kCC], uint32_t stage_addr, int nseg, int dy_hi, int dx_hi,
+__device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t stage_addr, int nseg, int dy_hi, int dx_hi,
                                               int wrow, int wcol) {
     const int lane = threadIdx.x & 31;
     const uint32_t aux = stage_addr + kHdrBytes;
     const uint32_t rowtab = aux + kAuxBytes;
     const uint32_t tile = rowtab + kRowTabBytes;
+    // The two compute warps that share an SM sub-partition (warp ids w and w + 4) walk the segments in opposite
+    // orders: otherwise they run the same instruction sequence in lockstep and their load phases coincide.
+    const bool reverse = (wrow & 4) != 0;
 #pragma unroll 1
-    for (int sg = 0; sg < nseg; ++sg) {
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+        const int sg = reverse ? nseg - 1 - sgi : sgi;
         int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, woff} as two words
         lds_entry(aux + 8u * (uint32_t)sg, reinterpret_cast<float&>(raw0), raw1);
         const int seg_dx0 = (int)(short)(raw0 & 0xffff), seg_dy0 = raw0 >> 16;
         const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
-        const int colbase = wcol * (32 * kCC) + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
+        const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
         const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
         const int sr0 = wrow * kR - seg_dy0 + dy_hi;      // staged row of output row 0 at step 0
         uint32_t wp = aux + kChunkSegBytes + 16u * (uint32_t)seg_woff;
         float4 wv[2];
         wv[0] = lds_v4(wp);
-        float win[kR][kWinW];
+        float2 win[kR][kWinW];
 #pragma unroll
         for (int r = 0; r < kR; ++r) load_row(win[r], tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + r)));
         int ro_next = 0;
@@ -446,7 +460,7 @@ __device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int ske
     const int k0 = (skew + 3) >> 2, k1 = (wv + skew) >> 2;
     const int head = min(4 * k0 - skew, wv), tail0 = max(4 * k1 - skew, head);
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < (kWarpW + 3 + 127) / 128; ++it) {
         const int k = lane + 32 * it;
         if (k >= k0 && k < k1) *reinterpret_cast<float4*>(g + (4 * k - skew)) = lds_v4(srow + 16u * (uint32_t)k);
     }
@@ -456,9 +470,9 @@ __device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int ske
 
 template <bool kEpi>
 __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0,
-                                           float (&acc)[kR][kCC], uint32_t obuf) {
+                                           float2 (&acc)[kR][kCC], uint32_t obuf) {
     const int lane = threadIdx.x & 31;
-    const int wv = min(32 * kCC, im.W - col0);
+    const int wv = min(kWarpW, im.W - col0);
     Epilogue ep;
     ep.flags = im.epilogue;
     ep.noise_sd = im.noise_sd;
@@ -478,11 +492,17 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
         const uint32_t b0 = obuf, b1 = obuf + 4u * kOutPitch;
         if (r < nrows) {
 #pragma unroll
-            for (int c = 0; c < kCC; ++c) sts_f32(b0 + 4u * (uint32_t)(skew0 + kCC * lane + c), acc[r][c]);
+            for (int c = 0; c < kCC; ++c) {
+                sts_f32(b0 + 4u * (uint32_t)(skew0 + kCC * lane + c), acc[r][c].x);
+                sts_f32(b0 + 4u * (uint32_t)(skew0 + kBlockStride + kCC * lane + c), acc[r][c].y);
+            }
         }
         if (r + 1 < nrows) {
 #pragma unroll
-            for (int c = 0; c < kCC; ++c) sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), acc[r + 1][c]);
+            for (int c = 0; c < kCC; ++c) {
+                sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), acc[r + 1][c].x);
+                sts_f32(b1 + 4u * (uint32_t)(skew1 + kBlockStride + kCC * lane + c), acc[r + 1][c].y);
+            }
         }
         __syncwarp();
         float* g1 = g + im.dst_rp;
@@ -568,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
         // ------------------------------------------------ compute warps
         const int wrow = warp / kWarpCols, wcol = warp % kWarpCols;
-        float acc[kR][kCC];
+        float2 acc[kR][kCC];
         const uint32_t obuf = smem_u32(obuf_all + warp * 2 * kOutPitch);
         for (int n = 0;; ++n) {
             const int b = n & 1;
@@ -587,10 +607,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
 #pragma unroll
                 for (int r = 0; r < kR; ++r)
 #pragma unroll
-                    for (int c = 0; c < kCC; ++c) acc[r][c] = 0.0f;
+                    for (int c = 0; c < kCC; ++c) acc[r][c] = make_float2(0.0f, 0.0f);
             }
             const TiledImage& im = p.img[h.img];
-            const int row0 = h.i0 + wrow * kR, col0 = h.j0 + wcol * (32 * kCC);
+            const int row0 = h.i0 + wrow * kR, col0 = h.j0 + wcol * kWarpW;
             const bool active = row0 < im.H && col0 < im.W;                       // warp-uniform
             if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
             __syncwarp();
