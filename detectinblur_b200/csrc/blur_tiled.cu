@@ -28,24 +28,28 @@
 
 namespace dib {
 
-// Shape of the register tiling.  Every thread owns two kR x kCC output blocks that sit kBlockStride columns apart in the
-// same rows; the pair shares weights, control flow and addressing, and every multiply-add is a packed FFMA2
-// (fma.rn.f32x2: one issue slot, two FMAs -- measured 62 TFLOP/s at 8 warps/SM where 3-register FFMA reaches 50), which
-// leaves the other issue slots to the window loads and the sweep control.  The unrolled sweep body is
-// kR (rotations) x kGroupW (tap columns) x kR * kCC FFMA2 of 16 bytes = 7 KB: it has to stay in the instruction cache
-// (a 29 KB body stalled on instruction fetch as often as it issued, profiles/round1_notes.md).
+// Shape of the register tiling.  Every thread owns a 2*kR-row x kCC-column output block and treats rows r and r + kR
+// as a PAIR: their accumulators share a 64-bit register and every multiply-add is a packed FFMA2 (fma.rn.f32x2: one
+// issue slot, two FMAs -- measured 62 TFLOP/s at 8 warps/SM where 3-register FFMA reaches 50), which leaves issue
+// slots for the window loads and the sweep control.  The pair's input rows are the same sliding window kR steps
+// apart, so one new row per step feeds both halves.  The unrolled sweep body is 2*kR (rotations) x kGroupW (tap
+// columns) x kR * kCC FFMA2 of 16 bytes = 14 KB: it has to stay in the instruction cache (a 29 KB body stalled on
+// instruction fetch as often as it issued, profiles/round1_notes.md).
 #ifndef DIB_R
 #define DIB_R 4
 #endif
 #ifndef DIB_WARP_ROWS
-#define DIB_WARP_ROWS 8
+#define DIB_WARP_ROWS 4
 #endif
-constexpr int kR = DIB_R;                   // output rows per thread (= rotation period of the register window)
-constexpr int kCC = 7;                      // output columns per block (odd: conflict-free lane stride)
-constexpr int kBlockStride = 32 * kCC;      // 224: column distance of a thread's two blocks
-constexpr int kWarpW = 2 * kBlockStride;    // 448 output columns per warp
-constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps stack vertically over the tile
-constexpr int kWarpCols = 1;
+#ifndef DIB_WARP_COLS
+#define DIB_WARP_COLS 2
+#endif
+constexpr int kR = DIB_R;                   // row pairs per thread
+constexpr int kRows = 2 * kR;               // output rows per thread (= rotation period of the register window)
+constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
+constexpr int kWarpW = 32 * kCC;            // 224 output columns per warp
+constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps are arranged kWarpRows x kWarpCols over the tile
+constexpr int kWarpCols = DIB_WARP_COLS;
 constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: equal load on the 4 SM sub-partitions
 constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
@@ -53,8 +57,8 @@ constexpr int kProducerRegs = 40;           // setmaxnreg budgets; together they
 constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8 > 232
                                  ? 232
                                  : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
-static_assert(kComputeWarps % 4 == 0 && kR % 2 == 0, "warpgroup-aligned compute warps, rows stored in pairs");
-constexpr int kTH = kWarpRows * kR;         // 32 output rows per tile
+static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
+constexpr int kTH = kWarpRows * kRows;      // 32 output rows per tile
 constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
 constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
 constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
@@ -171,7 +175,7 @@ struct __align__(16) StageHdr {
     int tile;           // global tile index; -1 = no more work
     int img, ch, i0, j0;
     int first_chunk, last_chunk;
-    int dy_hi, dx_hi, nseg;
+    int dy_hi, dx_hi, nseg, wsteps;
 };
 static_assert(sizeof(StageHdr) <= kHdrBytes, "stage header too large");
 
@@ -278,7 +282,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
         h.first_chunk = (st.chunk == 0);
         h.last_chunk = (st.chunk + 1 == im.nchunks);
-        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg;
+        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
         *sm.hdr = h;
     }
     uint32_t bytes = 0;
@@ -329,7 +333,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
 }
 
 // ---------------------------------------------------------------- compute
-// Packed pair of fp32 values: .x belongs to the thread's left block, .y to the block kBlockStride columns to the right.
+// Packed pair of fp32 values: .x belongs to output row r of the thread's block, .y to row r + kR.
 __device__ __forceinline__ float2 ffma2(float w, float2 x, float2 a) {
     unsigned long long d, ww, xx, aa;
     asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
@@ -341,34 +345,62 @@ __device__ __forceinline__ float2 ffma2(float w, float2 x, float2 a) {
     return r;
 }
 
-// One tap of a sweep step: weight w multiplies the window shifted by E columns.  Logical window row r sits in
-// register slot (r - U) mod kR.  Row 0 -- the row loaded at the start of this step -- is consumed last, so the FMAs
-// on the older rows cover that load's latency.
+// The window holds the kRows input rows of the current step.  Logical row q sits in slot (q - U) mod kRows at
+// rotation U; slot j < kR is win[j].x, slot j + kR is win[j].y, so the two rows of a pair (q and q + kR) always share
+// one 64-bit register -- in swapped halves for half of the rotations, which FFMA2's operand swizzle absorbs.
+template <int U, int Q>
+__device__ __forceinline__ float2 window_pair(const float2 (&win)[kR][kWinW], int k) {
+    constexpr int slot = ((Q - U) % kRows + kRows) % kRows;
+    if constexpr (slot < kR)
+        return win[slot][k];
+    else
+        return make_float2(win[slot - kR][k].y, win[slot - kR][k].x);
+}
+
+// One tap of a sweep step: weight w multiplies the window shifted by E columns.  Pair 0 contains the row loaded at
+// the start of this step and is consumed last, so the FMAs on the older rows cover that load's latency.
 template <int U, int E>
 __device__ __forceinline__ void fma_tap(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kWinW], const float w) {
 #pragma unroll
     for (int rr = 1; rr <= kR; ++rr) {
         const int r = rr % kR;
 #pragma unroll
-        for (int c = 0; c < kCC; ++c) acc[r][c] = ffma2(w, win[(r - U + kR) % kR][c - E + kGroupW - 1], acc[r][c]);
+        for (int c = 0; c < kCC; ++c) {
+            float2 x;
+            // constexpr dispatch on the pair index (r is a compile-time constant after unrolling)
+            if (r == 0) x = window_pair<U, 0>(win, c - E + kGroupW - 1);
+            else if (r == 1) x = window_pair<U, 1>(win, c - E + kGroupW - 1);
+            else if (r == 2) x = window_pair<U, 2>(win, c - E + kGroupW - 1);
+            else x = window_pair<U, 3>(win, c - E + kGroupW - 1);
+            acc[r][c] = ffma2(w, x, acc[r][c]);
+        }
     }
 }
+static_assert(kR <= 4, "fma_tap dispatches on at most 4 row pairs");
 
-__device__ __forceinline__ void load_row(float2 (&dst)[kWinW], uint32_t addr) {
+// load one input row into window slot SLOT
+template <int SLOT>
+__device__ __forceinline__ void load_row(float2 (&win)[kR][kWinW], uint32_t addr) {
 #pragma unroll
     for (int k = 0; k < kWinW; ++k) {
-        dst[k].x = lds_f32(addr + 4 * k);
-        dst[k].y = lds_f32(addr + 4 * (k + kBlockStride));
+        if constexpr (SLOT < kR)
+            win[SLOT][k].x = lds_f32(addr + 4 * k);
+        else
+            win[SLOT - kR][k].y = lds_f32(addr + 4 * k);
     }
 }
 
-// Step s of a segment sweep, s mod kR == U: fetch the new top row into the slot the previous step freed and the
-// NEXT step's weight vector (kR is even, so the two weight registers simply alternate), then accumulate the taps
+// Step s of a segment sweep, s mod kRows == U: fetch the new top row into the slot the previous step freed and the
+// NEXT step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate the taps
 // present in this step's vector; absent taps are skipped with warp-uniform branches.
+// Step s of a segment sweep, s mod kRows == U: fetch the new top row into the slot the previous step freed and the
+// NEXT step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate the taps
+// present in this step's vector; absent taps are skipped with warp-uniform branches.  (A fall-through chain driven by
+// per-step first/last codes was tried: the compiler's nested reconvergence scaffolding made it slower.)
 template <int U>
 __device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
                                            int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
-    if (s > 0) load_row(win[(kR - U) % kR], tile_cb + 4u * (uint32_t)ro_next);
+    if (s > 0) load_row<(kRows - U) % kRows>(win, tile_cb + 4u * (uint32_t)ro_next);
     ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
     wp += 16;
     wv[(U + 1) & 1] = lds_v4(wp);                                         // weights of step s + 1 (zero vector past the end)
@@ -381,13 +413,20 @@ __device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)
     return s < nsteps;
 }
 
-// kR consecutive steps = one full rotation of the window registers
+// step 0 needs all kRows rows: logical row q -> slot q
+template <int Q>
+__device__ __forceinline__ void fill_window(float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab, int sr0) {
+    load_row<Q>(win, tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + Q)));
+    if constexpr (Q + 1 < kRows) fill_window<Q + 1>(win, tile_cb, rowtab, sr0);
+}
+
+// kRows consecutive steps = one full rotation of the window registers
 template <int U>
 struct SweepRound {
     __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
                                                int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
         if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) return false;
-        if constexpr (U + 1 < kR)
+        if constexpr (U + 1 < kRows)
             return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv);
         else
             return true;
@@ -402,7 +441,7 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
     const uint32_t tile = rowtab + kRowTabBytes;
     // The two compute warps that share an SM sub-partition (warp ids w and w + 4) walk the segments in opposite
     // orders: otherwise they run the same instruction sequence in lockstep and their load phases coincide.
-    const bool reverse = (wrow & 4) != 0;
+    const bool reverse = ((threadIdx.x >> 5) & 4) != 0;
 #pragma unroll 1
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int sg = reverse ? nseg - 1 - sgi : sgi;
@@ -412,13 +451,12 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
         const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
         const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
-        const int sr0 = wrow * kR - seg_dy0 + dy_hi;      // staged row of output row 0 at step 0
+        const int sr0 = wrow * kRows - seg_dy0 + dy_hi;   // staged row of output row 0 at step 0
         uint32_t wp = aux + kChunkSegBytes + 16u * (uint32_t)seg_woff;
         float4 wv[2];
         wv[0] = lds_v4(wp);
         float2 win[kR][kWinW];
-#pragma unroll
-        for (int r = 0; r < kR; ++r) load_row(win[r], tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + r)));
+        fill_window<0>(win, tile_cb, rowtab, sr0);
         int ro_next = 0;
         int s = 0;
 #pragma unroll 1
@@ -483,26 +521,23 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
     const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
     uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
     const uint32_t rp_lo = (uint32_t)im.dst_rp;
-    const int nrows = min(kR, im.H - row0);
+    const int nrows = min(kRows, im.H - row0);
     // two rows per pass: accumulators -> the warp's two row buffers (each skewed so that shared and global addresses
-    // agree mod 16 bytes: element x of a row sits at buffer[skew + x]), then 16-byte stores of both rows
+    // agree mod 16 bytes: element x of a row sits at buffer[skew + x]), then 16-byte stores of both rows.
+    // Output row q is the .x half of pair q for q < kR and the .y half of pair q - kR otherwise.
 #pragma unroll
-    for (int r = 0; r < kR; r += 2) {
+    for (int r = 0; r < kRows; r += 2) {
         const int skew0 = (int)(phase & 3u), skew1 = (int)((phase + rp_lo) & 3u);
         const uint32_t b0 = obuf, b1 = obuf + 4u * kOutPitch;
         if (r < nrows) {
 #pragma unroll
-            for (int c = 0; c < kCC; ++c) {
-                sts_f32(b0 + 4u * (uint32_t)(skew0 + kCC * lane + c), acc[r][c].x);
-                sts_f32(b0 + 4u * (uint32_t)(skew0 + kBlockStride + kCC * lane + c), acc[r][c].y);
-            }
+            for (int c = 0; c < kCC; ++c)
+                sts_f32(b0 + 4u * (uint32_t)(skew0 + kCC * lane + c), r < kR ? acc[r % kR][c].x : acc[r % kR][c].y);
         }
         if (r + 1 < nrows) {
 #pragma unroll
-            for (int c = 0; c < kCC; ++c) {
-                sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), acc[r + 1][c].x);
-                sts_f32(b1 + 4u * (uint32_t)(skew1 + kBlockStride + kCC * lane + c), acc[r + 1][c].y);
-            }
+            for (int c = 0; c < kCC; ++c)
+                sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), r + 1 < kR ? acc[(r + 1) % kR][c].x : acc[(r + 1) % kR][c].y);
         }
         __syncwarp();
         float* g1 = g + im.dst_rp;
@@ -597,10 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             StageHdr h;
             {   // explicit vector loads keep the header in registers
                 const int4 a = reinterpret_cast<const int4*>(sm.hdr)[0], b4 = reinterpret_cast<const int4*>(sm.hdr)[1];
-                const int2 c2 = reinterpret_cast<const int2*>(sm.hdr)[4];
+                const int4 c2 = reinterpret_cast<const int4*>(sm.hdr)[2];
                 h.tile = a.x; h.img = a.y; h.ch = a.z; h.i0 = a.w;
                 h.j0 = b4.x; h.first_chunk = b4.y; h.last_chunk = b4.z; h.dy_hi = b4.w;
-                h.dx_hi = c2.x; h.nseg = c2.y;
+                h.dx_hi = c2.x; h.nseg = c2.y; h.wsteps = c2.z;
             }
             if (h.tile < 0) break;
             if (h.first_chunk) {
@@ -610,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
                     for (int c = 0; c < kCC; ++c) acc[r][c] = make_float2(0.0f, 0.0f);
             }
             const TiledImage& im = p.img[h.img];
-            const int row0 = h.i0 + wrow * kR, col0 = h.j0 + wcol * kWarpW;
+            const int row0 = h.i0 + wrow * kRows, col0 = h.j0 + wcol * kWarpW;
             const bool active = row0 < im.H && col0 < im.W;                       // warp-uniform
             if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
             __syncwarp();
