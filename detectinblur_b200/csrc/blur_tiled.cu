@@ -3,7 +3,7 @@
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
 // persistent, warp-specialised launch per batch:
-//   * work unit  = one 32 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
+//   * work unit  = one 36 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
 //                  global ticket counter, images with the heaviest PSFs first;
 //   * producer   = one warp.  For every stage (tile x program chunk) it stages tile + halo global -> shared:
 //                  TMA bulk copies (cp.async.bulk, one per tile row, the 16-byte-aligned interior of the row
@@ -33,13 +33,16 @@ namespace dib {
 // issue slot, two FMAs -- measured 62 TFLOP/s at 8 warps/SM where 3-register FFMA reaches 50), which leaves issue
 // slots for the window loads and the sweep control.  The pair's input rows are the same sliding window kR steps
 // apart, so one new row per step feeds both halves.  The unrolled sweep body is 2*kR (rotations) x kGroupW (tap
-// columns) x kR * kCC FFMA2 of 16 bytes = 14 KB: it has to stay in the instruction cache (a 29 KB body stalled on
-// instruction fetch as often as it issued, profiles/round1_notes.md).
+// columns) x kR * kCC FFMA2 of 16 bytes = 8 KB: it has to stay in the instruction cache (a 29 KB body stalled on
+// instruction fetch as often as it issued, profiles/round1_notes.md).  kR = 3 keeps a compute thread at ~130
+// registers, so 12 compute warps (three per SM sub-partition) fit beside the producer warpgroup; kR = 4 needs 172
+// registers, allows only 8 compute warps and measured 5 % slower; kR = 2 with 16 warps deadlocked on the box and
+// was not pursued.
 #ifndef DIB_R
-#define DIB_R 4
+#define DIB_R 3
 #endif
 #ifndef DIB_WARP_ROWS
-#define DIB_WARP_ROWS 4
+#define DIB_WARP_ROWS 6
 #endif
 #ifndef DIB_WARP_COLS
 #define DIB_WARP_COLS 2
@@ -58,7 +61,7 @@ constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (k
                                  ? 232
                                  : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
 static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
-constexpr int kTH = kWarpRows * kRows;      // 32 output rows per tile
+constexpr int kTH = kWarpRows * kRows;      // 36 output rows per tile
 constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
 constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
 constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
