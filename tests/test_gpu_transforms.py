@@ -151,3 +151,58 @@ def test_philox_noise_statistics(cuda):
         assert torch.equal(out, again)          # counter-based: same seed, same noise
         other = bf.blur_batch([img], ts, [0], noise_sd=[sd], philox_seed=99, exact=exact)[0]
         assert not torch.equal(out, other)
+
+
+def test_estimator_mirror_and_bank_writer(cuda, golden_dir, tmp_path):
+    import detectinblur_b200.engine_blur_estimator as est
+    from detectinblur_b200 import psf_bank
+    g = np.load(os.path.join(golden_dir, "estimator_cases.npz"), allow_pickle=False)
+    psf = torch.from_numpy(g["psf"]).to(cuda)
+    psfn = psf / psf.sum()
+    for n in range(int(g["n"])):
+        img = torch.from_numpy(g["img_%d" % n]).to(cuda)
+        got = est.manual_blur(img, psfn, resize_images=True).cpu().numpy()
+        want = g["out_%d" % n]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 3e-5, n       # GPU bilinear resize + tiled blur vs the reference on CPU
+        lst = [img]
+        est.blur_image_list(lst, [{"blurring": True}], [psf], resize_images=True)
+        assert np.abs(lst[0].cpu().numpy() - want).max() <= 3e-5
+    with pytest.raises(NotImplementedError):
+        est.manual_blur(torch.rand(3, 900, 100, device=cuda), psfn, resize_images=True)
+    # bank writer: byte-identical to what dataset_utils/generate_PSFs.py stores (oracle = the pinned restatement)
+    dest = str(tmp_path) + "/"
+    n_written = psf_bank.generate_psf_bank(dest, worker_index=1, num_workers=2, total_num_psfs=4, device=cuda)
+    assert n_written == 3 * 5 * 2
+    np.random.seed(1337 * 1)
+    for p, expl in enumerate(psf_bank.PARAMS):
+        for e, frac in enumerate(psf_bank.FRACTIONS):
+            for index in (2, 3):
+                want, _ = po.stored_psf(expl, frac, np.random)
+                path = dest + "psfs/P%dE%d/I%06d" % (p + 1, e, index)
+                got = np.load(open(path, "rb"))
+                assert got.dtype == np.float16 and got.shape == (256, 256) and np.array_equal(got, want), path
+                assert np.array_equal(psf_bank.load_stored_psf(dest + "psfs", p + 1, e, index), want[64:192, 64:192])
+
+
+def test_eval_sweep_shapes_tiled_vs_exact(cuda):
+    """BASELINE config 4: P in {0.005, 0.001, 0.00005} x E in {1/25, 1/10, 1/5, 1/2, 1} (evaluate.py:299-300) on
+    COCO-val-like shapes: rasterise on the GPU, blur with the tiled kernel, compare with the exact-order kernel."""
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+    from detectinblur_b200.motion_blur import Trajectory
+    shapes = [(480, 640), (427, 640), (640, 480), (640, 427), (375, 500), (500, 375), (333, 500)]
+    np.random.seed(2024)
+    traj, frac = [], []
+    for expl in (0.005, 0.001, 0.00005):
+        for f in (1 / 25, 1 / 10, 1 / 5, 1 / 2, 1):
+            traj.append(Trajectory(canvas=256, max_len=96, expl=expl).fit().fit().x)
+            frac.append(f)
+    psfs = ops.rasterize_psfs(np.stack(traj), frac, cuda, dtype=torch.float32)
+    ts = ops.compact_taps(psfs, normalize=True)
+    g = torch.Generator().manual_seed(7)
+    imgs = [torch.rand((3,) + shapes[k % len(shapes)], generator=g).to(cuda) for k in range(15)]
+    fast = bf.blur_batch(imgs, ts, list(range(15)), exact=False)
+    exact = bf.blur_batch(imgs, ts, list(range(15)), exact=True)
+    for k in range(15):
+        assert (fast[k].double() - exact[k].double()).abs().max().item() <= 1e-5, (k, ts.counts[k])

@@ -105,3 +105,26 @@ def test_fourier_port(golden_dir):
 def test_normalize(golden_dir):
     g = _load(golden_dir, "normalize_case.npz")
     assert np.array_equal(bo.normalize_image(g["img"], g["mean"], g["std"]), g["out"])
+
+
+def test_estimator_resize_variant(golden_dir):
+    """engine_blur_estimator.manual_blur(resize_images=True): bilinear resize (torch, as the reference) around the oracle blur."""
+    import torch
+    g = _load(golden_dir, "estimator_cases.npz")
+    psfn = bo.normalize_psf(g["psf"])
+    for n in range(int(g["n"])):
+        img = g["img_%d" % n]
+        C, H, W = img.shape
+        x = torch.from_numpy(img)[None]
+        if H > W:
+            x = x.permute(0, 1, 3, 2)
+            size = (800, int(800 * H / W))
+        else:
+            size = (800, int(800 * W / H))
+        big = torch.nn.functional.interpolate(x, size=size, mode="bilinear")[0].numpy()
+        blurred = bo.manual_blur(big, psfn)
+        if blurred.ndim == 2:
+            blurred = blurred[None]
+        want = g["out_%d" % n]
+        got = blurred[:, :H, :W]
+        assert np.array_equal(np.squeeze(got), want), n

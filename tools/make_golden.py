@@ -261,6 +261,28 @@ def gen_normalize_case():
     print("normalize case: 1")
 
 
+def gen_estimator_cases():
+    """engine_blur_estimator.manual_blur with resize_images (:27-70).  The module itself cannot be imported here (it pulls in
+    pycocotools), so the two function definitions are executed from the reference file at run time; nothing is copied."""
+    import math
+    src = open(os.path.join(refshim.install(), "engine_blur_estimator.py")).read().split("\n")
+    ns = {"torch": torch, "math": math}
+    exec("\n".join(src[26:79]), ns)
+    cases = {}
+    _, _, cen = ref_psf(0.005, 1 / 10, 77)
+    psf = cen.astype(np.float16)[64:192, 64:192].astype(np.float32)
+    psfn = torch.from_numpy(psf) / torch.from_numpy(psf).sum()
+    rng = np.random.default_rng(77)
+    for n, (C, H, W) in enumerate([(3, 120, 200), (3, 200, 120), (1, 90, 90)]):
+        img = rng.random((C, H, W), dtype=np.float32)
+        out = ns["manual_blur"](torch.from_numpy(img), psfn, True)
+        cases["img_%d" % n], cases["out_%d" % n] = img, out.contiguous().numpy()
+    cases["psf"] = psf
+    cases["n"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "estimator_cases.npz"), **cases)
+    print("estimator cases: 3")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_psf_cases()
@@ -268,3 +290,4 @@ if __name__ == "__main__":
     gen_transform_cases()
     gen_fourier_case()
     gen_normalize_case()
+    gen_estimator_cases()
