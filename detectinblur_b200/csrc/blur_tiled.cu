@@ -47,6 +47,9 @@ namespace dib {
 #ifndef DIB_WARP_COLS
 #define DIB_WARP_COLS 2
 #endif
+#ifndef DIB_PRODUCER_REGS
+#define DIB_PRODUCER_REGS 40
+#endif
 constexpr int kR = DIB_R;                   // row pairs per thread
 constexpr int kRows = 2 * kR;               // output rows per thread (= rotation period of the register window)
 constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
@@ -56,7 +59,7 @@ constexpr int kWarpCols = DIB_WARP_COLS;
 constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: equal load on the 4 SM sub-partitions
 constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
-constexpr int kProducerRegs = 40;           // setmaxnreg budgets; together they must fit the 64K-register file
+constexpr int kProducerRegs = DIB_PRODUCER_REGS;   // setmaxnreg budgets; together they must fit the 64K-register file
 constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8 > 232
                                  ? 232
                                  : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
@@ -313,7 +316,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
     if (sr < kRowsMax) sm.rowtab[sr] = ro;   // rows past a partial tile are read (results discarded): offsets stay in range
     if (pt == 32) {
-        const uint32_t nb = (uint32_t)(kChunkSegBytes + 16 * (st.rec.wsteps + 1));
+        const uint32_t nb = (uint32_t)(kChunkSegBytes + kStepBytes * (st.rec.wsteps + 1));
         tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, bar);
         bytes += nb;
     }
@@ -400,18 +403,35 @@ __device__ __forceinline__ void load_row(float2 (&win)[kR][kWinW], uint32_t addr
 // NEXT step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate the taps
 // present in this step's vector; absent taps are skipped with warp-uniform branches.  (A fall-through chain driven by
 // per-step first/last codes was tried: the compiler's nested reconvergence scaffolding made it slower.)
+// the kGroupW weights of one step
+struct WeightVec {
+    float4 q[kGroupW / 4];
+};
+__device__ __forceinline__ WeightVec lds_weights(uint32_t addr) {
+    WeightVec w;
+#pragma unroll
+    for (int i = 0; i < kGroupW / 4; ++i) w.q[i] = lds_v4(addr + 16u * i);
+    return w;
+}
+
 template <int U>
 __device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                           int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
+                                           int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, WeightVec (&wv)[2]) {
     if (s > 0) load_row<(kRows - U) % kRows>(win, tile_cb + 4u * (uint32_t)ro_next);
     ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
-    wp += 16;
-    wv[(U + 1) & 1] = lds_v4(wp);                                         // weights of step s + 1 (zero vector past the end)
-    const float4 w = wv[U & 1];
-    if (w.x != 0.0f) fma_tap<U, 0>(acc, win, w.x);
-    if (w.y != 0.0f) fma_tap<U, 1>(acc, win, w.y);
-    if (w.z != 0.0f) fma_tap<U, 2>(acc, win, w.z);
-    if (w.w != 0.0f) fma_tap<U, 3>(acc, win, w.w);
+    wp += kStepBytes;
+    wv[(U + 1) & 1] = lds_weights(wp);                                    // weights of step s + 1 (zero vector past the end)
+    const WeightVec& w = wv[U & 1];
+    if (w.q[0].x != 0.0f) fma_tap<U, 0>(acc, win, w.q[0].x);
+    if (w.q[0].y != 0.0f) fma_tap<U, 1>(acc, win, w.q[0].y);
+    if (w.q[0].z != 0.0f) fma_tap<U, 2>(acc, win, w.q[0].z);
+    if (w.q[0].w != 0.0f) fma_tap<U, 3>(acc, win, w.q[0].w);
+    if constexpr (kGroupW == 8) {
+        if (w.q[kGroupW / 4 - 1].x != 0.0f) fma_tap<U, 4>(acc, win, w.q[kGroupW / 4 - 1].x);
+        if (w.q[kGroupW / 4 - 1].y != 0.0f) fma_tap<U, 5>(acc, win, w.q[kGroupW / 4 - 1].y);
+        if (w.q[kGroupW / 4 - 1].z != 0.0f) fma_tap<U, 6>(acc, win, w.q[kGroupW / 4 - 1].z);
+        if (w.q[kGroupW / 4 - 1].w != 0.0f) fma_tap<U, 7>(acc, win, w.q[kGroupW / 4 - 1].w);
+    }
     ++s;
     return s < nsteps;
 }
@@ -427,7 +447,7 @@ __device__ __forceinline__ void fill_window(float2 (&win)[kR][kWinW], uint32_t t
 template <int U>
 struct SweepRound {
     __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                               int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, float4 (&wv)[2]) {
+                                               int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, WeightVec (&wv)[2]) {
         if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) return false;
         if constexpr (U + 1 < kRows)
             return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv);
@@ -455,9 +475,9 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
         const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
         const int sr0 = wrow * kRows - seg_dy0 + dy_hi;   // staged row of output row 0 at step 0
-        uint32_t wp = aux + kChunkSegBytes + 16u * (uint32_t)seg_woff;
-        float4 wv[2];
-        wv[0] = lds_v4(wp);
+        uint32_t wp = aux + kChunkSegBytes + (uint32_t)kStepBytes * (uint32_t)seg_woff;
+        WeightVec wv[2];
+        wv[0] = lds_weights(wp);
         float2 win[kR][kWinW];
         fill_window<0>(win, tile_cb, rowtab, sr0);
         int ro_next = 0;

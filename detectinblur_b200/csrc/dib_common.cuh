@@ -35,8 +35,12 @@ void set_error(const char* fmt, ...);
 // vector per row ("step"; zero where the PSF has no tap -- the kernel skips those with uniform branches).  Segments
 // are packed into CHUNKS whose tap extents are bounded (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that
 // tile + halo of any chunk fits the kernel's fixed shared-memory stage, whatever the PSF's overall extent.
-constexpr int kGroupW = 4;              // PSF columns per group (one float4 of weights per step)
-constexpr int kChunkGroups = 5;         // groups per chunk  -> column halo <= 19
+#ifndef DIB_GW
+#define DIB_GW 4
+#endif
+constexpr int kGroupW = DIB_GW;         // PSF columns per group (kGroupW / 4 float4 of weights per step)
+constexpr int kChunkGroups = 20 / kGroupW;   // groups per chunk  -> column halo <= 19 (GW 4) / 15 (GW 8)
+static_assert(kGroupW == 4 || kGroupW == 8, "weight vectors are read as float4");
 constexpr int kChunkHaloRows = 17;      // dy_hi - dy_lo per chunk
 constexpr int kProgMaxChunks = 32;
 struct SegRec {         // 8 bytes
@@ -55,7 +59,8 @@ struct ChunkRec {       // 16 bytes
 // chunk data block: SegRec slots (48 B, fixed) then float4[wsteps] (+ one zero vector: the kernel prefetches one ahead)
 constexpr int kChunkSegBytes = 48;
 constexpr int kChunkMaxSteps = kChunkGroups * (kChunkHaloRows + 1);                       // 90
-constexpr int kChunkDataMax = kChunkSegBytes + 16 * (kChunkMaxSteps + 1);                 // 1504
+constexpr int kStepBytes = 4 * kGroupW;                                                    // one weight vector
+constexpr int kChunkDataMax = kChunkSegBytes + kStepBytes * (kChunkMaxSteps + 1);
 constexpr size_t kProgHeaderBytes = sizeof(ChunkRec) * kProgMaxChunks;                    // 512
 constexpr size_t kProgDataBytes = 16384;
 constexpr size_t kProgBytes = kProgHeaderBytes + kProgDataBytes;

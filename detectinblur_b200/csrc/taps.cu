@@ -258,7 +258,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                         nw += sh_segs[ci * kChunkGroups + sgi].nsteps;
                     }
                     total_steps += nw;
-                    const int bytes = kChunkSegBytes + 16 * (nw + 1);
+                    const int bytes = kChunkSegBytes + kStepBytes * (nw + 1);
                     if (nw > kChunkMaxSteps || data_off + bytes > (int)kProgBytes) { ok = false; break; }
                     sh_chunks[ci].wsteps = (int16_t)nw;
                     sh_chunks[ci].data_off = data_off;

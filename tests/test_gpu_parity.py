@@ -265,3 +265,53 @@ def test_checksum(dib):
     with np.errstate(over="ignore"):
         want = mix64((idx << np.uint64(32)) ^ (idx >> np.uint64(32)) ^ (bits * np.uint64(0x9E3779B97F4A7C15)) ^ idx).sum(dtype=np.uint64)
     assert np.uint64(c1 & 0xFFFFFFFFFFFFFFFF) == want
+
+
+def test_mixed_batch_both_kernels_and_pitched_views(dib):
+    """One call with images for the tiled kernel, images only the exact-order kernel takes (zero-pad mode) and a
+    pass-through entry; inputs and outputs that are views with padded pitches (rows of a zero-padded batch)."""
+    bf, ops = dib
+    rng = np.random.default_rng(21)
+    np.random.seed(21)
+    psfs = []
+    for frac in (1 / 10, 1 / 5, 1 / 2):
+        p16, _ = po.stored_psf(0.001, frac, np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    ts = ops.compact_taps(_cuda(np.stack(psfs)), normalize=True)
+    shapes = [(3, 130, 470), (3, 40, 50), (3, 97, 131), (3, 90, 60)]
+    imgs = [rng.random(s, dtype=np.float32) for s in shapes]
+    big_in = torch.zeros((3, 160, 512)).cuda()
+    big_in[:, :130, :470] = _cuda(imgs[0])
+    srcs = [big_in[:, :130, :470], _cuda(imgs[1]), _cuda(imgs[2]), _cuda(imgs[3])]
+    big_out = torch.zeros((3, 128, 160)).cuda()
+    outs = [None, None, big_out[:, :97, :131], None]
+    idx = [0, 1, 2, -1]
+    l0 = bf.launch_count()
+    got = bf.blur_batch(srcs, ts, idx, outs=outs)
+    assert bf.launch_count() - l0 == 2            # one tiled launch + one exact-order launch
+    for k in range(3):
+        want = bo.manual_blur(imgs[k], bo.normalize_psf(psfs[idx[k]]))
+        g = got[k].cpu().numpy()
+        if shapes[k][1] < 64:
+            assert np.array_equal(g, want)         # zero-pad mode runs on the exact-order kernel
+        else:
+            assert np.abs(g - want).max() <= TOL_FP32, k
+    assert torch.equal(got[3], srcs[3])            # psf_index -1: passed through
+    assert big_out[:, 97:, :].abs().max().item() == 0 and big_out[:, :, 131:].abs().max().item() == 0
+
+
+def test_many_images_one_call(dib):
+    """More images than DIB_MAX_BATCH: the wrapper splits the call; every image still gets its own PSF."""
+    bf, ops = dib
+    n = 37
+    g = torch.Generator().manual_seed(3)
+    imgs = [torch.rand((3, 70 + k % 5, 80 + k % 7), generator=g).cuda() for k in range(n)]
+    psf = torch.zeros((n, 128, 128)).cuda()
+    for k in range(n):
+        psf[k, 63 + k % 3, 63 - k % 4] = 1.0       # one-tap PSFs: out = shifted image in the interior
+    ts = ops.compact_taps(psf, normalize=True)
+    outs = bf.blur_batch(imgs, ts, list(range(n)))
+    for k in range(n):
+        dy, dx = k % 3, -(k % 4)
+        H, W = imgs[k].shape[1:]
+        assert torch.equal(outs[k][:, 8:H - 8, 8:W - 8], imgs[k][:, 8 - dy:H - 8 - dy, 8 - dx:W - 8 - dx]), k
