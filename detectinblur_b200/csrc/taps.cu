@@ -72,6 +72,34 @@ __device__ inline int block_min_int(int v, int* sh) {
     return t;
 }
 
+constexpr int kMaxBands = (32 + kChunkGroups - 1) / kChunkGroups;   // <= 32 groups of kGroupW columns in a 128-wide PSF
+constexpr int kBandMaxChunks = 8;                                   // 128 rows / (kChunkHaloRows + 1) rounded up
+
+// first set bit at position >= from in a 128-bit mask (4 words, bit y of word y >> 5), or -1
+__device__ inline int mask_first_from(const unsigned* m, int from) {
+    for (int k = max(from, 0) >> 5; k < 4; ++k) {
+        unsigned w = m[k];
+        if (k == (from >> 5)) w &= 0xffffffffu << (from & 31);
+        if (w) return k * 32 + __ffs(w) - 1;
+    }
+    return -1;
+}
+
+// first and last set bit within [y0, y1] (f = -1 when none)
+__device__ inline void mask_range_first_last(const unsigned* m, int y0, int y1, int& f, int& l) {
+    f = -1;
+    l = -1;
+    for (int k = y0 >> 5; k <= (y1 >> 5) && k < 4; ++k) {
+        unsigned w = m[k];
+        if (k == (y0 >> 5)) w &= 0xffffffffu << (y0 & 31);
+        if (k == (y1 >> 5)) w &= 0xffffffffu >> (31 - (y1 & 31));
+        if (w) {
+            if (f < 0) f = k * 32 + __ffs(w) - 1;
+            l = k * 32 + 31 - __clz(w);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
@@ -84,6 +112,9 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ unsigned sh_occ[32 * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
     __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
+    __shared__ ChunkRec sh_band_chunks[kMaxBands * kBandMaxChunks];
+    __shared__ SegRec sh_band_segs[kMaxBands * kBandMaxChunks * kChunkGroups];
+    __shared__ int sh_band_count[kMaxBands];
     __shared__ int sh_nchunks, sh_nsegs, sh_total_steps;
 
     const int n = blockIdx.x;
@@ -101,55 +132,70 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const double total = block_sum_double(part, sh_d);
     const float s = PsfNum<T>::round_sum(total);
 
-    // 2. ordered compaction of the normalised PSF (row-major nonzero order, blur_functions.py:63)
-    if (tid == 0) sh_running = 0;
+    // 2. ordered compaction of the normalised PSF (row-major nonzero order, blur_functions.py:63).  Every warp owns a
+    //    contiguous slab of the PSF: pass 1 counts its taps (ballot + popc, no block barrier), one scan over the 8 warp
+    //    totals gives each slab its output offset, pass 2 writes the taps in order.
     int ymin = 1 << 20, ymax_neg = 1 << 20, xmin = 1 << 20, xmax_neg = 1 << 20;  // max kept as min of negatives
     long long sy = 0, sx = 0, syy = 0, sxx = 0, sxy = 0, support = 0;
-    __syncthreads();
-    for (int base = 0; base < cells; base += kCompactThreads) {
-        const int i = base + tid;
+    const int slab = ((cells + kCompactThreads / 32 - 1) / (kCompactThreads / 32) + 31) & ~31;
+    const int slab_lo = warp * slab, slab_hi = min(cells, slab_lo + slab);
+    int warp_count = 0;
+    for (int base = slab_lo; base < slab_hi; base += 32) {
+        const int i = base + lane;
         float v = 0.0f, w = 0.0f;
-        if (i < cells) {
+        if (i < slab_hi) {
             v = PsfNum<T>::load(psf, i);
             w = normalize ? PsfNum<T>::normalized(v, s) : v;
         }
         const bool nz = (w != 0.0f);
-        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
-        if (lane == 0) sh_warp_count[warp] = __popc(ballot);
-        __syncthreads();
-        int offset = sh_running;
-        for (int k = 0; k < warp; ++k) offset += sh_warp_count[k];
-        const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
-        const int y = i / side, x = i - y * side;
-        if (nz) {
-            if (pos < max_taps) {
-                dib_tap t;
-                t.y = (int16_t)y;
-                t.x = (int16_t)x;
-                t.w = w;
-                taps[(int64_t)n * max_taps + pos] = t;
+        warp_count += __popc(__ballot_sync(0xffffffffu, nz));
+        if (nz || v > 0.0f) {
+            const int y = i / side, x = i - y * side;
+            if (nz) {
+                ymin = min(ymin, y);
+                ymax_neg = min(ymax_neg, -y);
+                xmin = min(xmin, x);
+                xmax_neg = min(xmax_neg, -x);
             }
-            ymin = min(ymin, y);
-            ymax_neg = min(ymax_neg, -y);
-            xmin = min(xmin, x);
-            xmax_neg = min(xmax_neg, -x);
+            if (v > 0.0f) {  // support of the PCA: psf > 0 (transforms.py:366)
+                support += 1;
+                sy += y;
+                sx += x;
+                syy += (long long)y * y;
+                sxx += (long long)x * x;
+                sxy += (long long)y * x;
+            }
         }
-        if (i < cells && v > 0.0f) {  // support of the PCA: psf > 0 (transforms.py:366)
-            support += 1;
-            sy += y;
-            sx += x;
-            syy += (long long)y * y;
-            sxx += (long long)x * x;
-            sxy += (long long)y * x;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int c = 0;
-            for (int k = 0; k < kCompactThreads / 32; ++k) c += sh_warp_count[k];
-            sh_running += c;
-        }
-        __syncthreads();
     }
+    if (lane == 0) sh_warp_count[warp] = warp_count;
+    __syncthreads();
+    int offset = 0, total_count = 0;
+    for (int k = 0; k < kCompactThreads / 32; ++k) {
+        if (k < warp) offset += sh_warp_count[k];
+        total_count += sh_warp_count[k];
+    }
+    for (int base = slab_lo; base < slab_hi; base += 32) {
+        const int i = base + lane;
+        float w = 0.0f;
+        if (i < slab_hi) {
+            const float v = PsfNum<T>::load(psf, i);
+            w = normalize ? PsfNum<T>::normalized(v, s) : v;
+        }
+        const bool nz = (w != 0.0f);
+        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+        const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
+        if (nz && pos < max_taps) {
+            const int y = i / side, x = i - y * side;
+            dib_tap t;
+            t.y = (int16_t)y;
+            t.x = (int16_t)x;
+            t.w = w;
+            taps[(int64_t)n * max_taps + pos] = t;
+        }
+        offset += __popc(ballot);
+    }
+    if (tid == 0) sh_running = total_count;
+    __syncthreads();
     const int count = sh_running;
     ymin = block_min_int(ymin, sh_i);
     const int ymax = -block_min_int(ymax_neg, sh_i);
@@ -197,48 +243,61 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
         }
         __syncthreads();
-        // 3b. one thread cuts the support into chunks of segments (a few dozen iterations of bit scans)
+        // 3b. cut the support into chunks of segments: one thread per band of kChunkGroups groups walks that band's rows
+        //     with 128-bit masks (find-first-set), then thread 0 concatenates the bands' chunk lists in band order
+        const int nbands = (ngroups + kChunkGroups - 1) / kChunkGroups;
+        if (tid < nbands) {
+            const int g0 = tid * kChunkGroups, g1 = min(g0 + kChunkGroups, ngroups);
+            unsigned band[4] = {0u, 0u, 0u, 0u};
+            for (int g = g0; g < g1; ++g)
+                for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
+            int cursor = ymin, nb = 0;
+            while (nb < kBandMaxChunks) {
+                int y0 = mask_first_from(band, cursor);
+                if (y0 < 0) break;
+                const int y1 = min(y0 + kChunkHaloRows, ymax);
+                ChunkRec c;
+                int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
+                for (int g = g0; g < g1; ++g) {
+                    int f, l;
+                    mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
+                    if (f < 0) continue;
+                    SegRec sg;
+                    sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
+                    sg.dy0 = (int16_t)(f - centre);
+                    sg.nsteps = (int16_t)(l - f + 1);
+                    sg.woff = 0;
+                    lo = min(lo, f - centre);
+                    hi = max(hi, l - centre);
+                    xlo = min(xlo, (int)sg.dx0);
+                    xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
+                    sh_band_segs[(tid * kBandMaxChunks + nb) * kChunkGroups + nseg] = sg;
+                    ++nseg;
+                }
+                c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
+                c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
+                c.nseg = (int16_t)nseg; c.wsteps = 0;
+                c.data_off = 0;
+                sh_band_chunks[tid * kBandMaxChunks + nb] = c;
+                ++nb;
+                cursor = y1 + 1;
+            }
+            // more rows left than kBandMaxChunks chunks can cover: no program (the generic kernel takes the PSF)
+            sh_band_count[tid] = (nb == kBandMaxChunks && mask_first_from(band, cursor) >= 0) ? -1 : nb;
+        }
+        __syncthreads();
         if (tid == 0) {
             int nchunks = 0, nsegs = 0;
             bool ok = true;
-            for (int g0 = 0; g0 < ngroups && ok; g0 += kChunkGroups) {
-                const int g1 = min(g0 + kChunkGroups, ngroups);
-                int cursor = ymin;
-                while (ok) {
-                    int y0 = -1;   // first occupied row >= cursor in this band of groups
-                    for (int y = cursor; y <= ymax && y0 < 0; ++y)
-                        for (int g = g0; g < g1; ++g)
-                            if ((sh_occ[g * 4 + (y >> 5)] >> (y & 31)) & 1u) { y0 = y; break; }
-                    if (y0 < 0) break;
-                    const int y1 = min(y0 + kChunkHaloRows, ymax);
-                    if (nchunks >= kProgMaxChunks) { ok = false; break; }
-                    ChunkRec c;
-                    int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
-                    for (int g = g0; g < g1; ++g) {
-                        int f = -1, l = -1;
-                        for (int y = y0; y <= y1; ++y)
-                            if ((sh_occ[g * 4 + (y >> 5)] >> (y & 31)) & 1u) { if (f < 0) f = y; l = y; }
-                        if (f < 0) continue;
-                        SegRec sg;
-                        sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
-                        sg.dy0 = (int16_t)(f - centre);
-                        sg.nsteps = (int16_t)(l - f + 1);
-                        sg.woff = 0;
-                        lo = min(lo, f - centre);
-                        hi = max(hi, l - centre);
-                        xlo = min(xlo, (int)sg.dx0);
-                        xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
-                        sh_segs[nchunks * kChunkGroups + nseg] = sg;
-                        ++nseg;
-                        ++nsegs;
-                    }
-                    c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
-                    c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
-                    c.nseg = (int16_t)nseg; c.wsteps = 0;
-                    c.data_off = 0;
-                    sh_chunks[nchunks] = c;
+            for (int bnd = 0; bnd < nbands && ok; ++bnd) {
+                const int nb = sh_band_count[bnd];
+                if (nb < 0 || nchunks + nb > kProgMaxChunks) { ok = false; break; }
+                for (int k = 0; k < nb; ++k) {
+                    sh_chunks[nchunks] = sh_band_chunks[bnd * kBandMaxChunks + k];
+                    for (int q = 0; q < kChunkGroups; ++q)
+                        sh_segs[nchunks * kChunkGroups + q] = sh_band_segs[(bnd * kBandMaxChunks + k) * kChunkGroups + q];
+                    nsegs += sh_chunks[nchunks].nseg;
                     ++nchunks;
-                    cursor = y1 + 1;
                 }
             }
             sh_nchunks = ok ? nchunks : -1;
