@@ -9,9 +9,11 @@ for the whole list instead of O(taps) launches and two host syncs per tap per im
 Differences from the reference, all deliberate:
   * results are new contiguous tensors (the reference returns a crop view of its padded accumulator);
   * CUDA tensors only: there is no CPU path;
-  * fp32 images take the tiled kernel (FMA accumulation, <= 1e-5 from the reference loop; measured ~3e-7);
+  * fp32 images take the tiled kernel (FMA accumulation, <= 1e-5 from the reference loop; measured ~4e-7);
     ``exact=True`` (or ``DIB_EXACT=1``) forces the exact-order kernel, bit-identical to the reference's loop.
-    fp16 images always take the exact-order kernel, bit-identical to the reference's half loop.
+  * fp16 images (what the reference's engines pass) are widened, blurred with fp32 accumulation and rounded to half
+    once: within 5e-3 of the reference's half loop, which rounds after every tap; ``exact=True`` reproduces that loop
+    bit for bit on the exact-order kernel.
 """
 import ctypes
 import math
@@ -90,6 +92,8 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     exact = _exact_default() if exact is None else exact
     if n == 0:
         return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
+    if images[0].dtype == torch.float16 and not exact:
+        return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma)
     dev = images[0].device
     dtype = images[0].dtype
     if dtype not in _DT:
@@ -149,6 +153,31 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
         d.epilogue = epi
     algo = _lib.ALGO_GENERIC if exact else _lib.ALGO_AUTO
     return BlurPlan(descs, n, tapset, dtype, algo, philox_seed, dev, results, keep)
+
+
+class _HalfPlan(object):
+    """fp16 images on the fast path: widen to fp32, blur with fp32 accumulation (tiled kernel where eligible), round to
+    half ONCE.  More accurate than the reference's half loop, which rounds after every tap (it differs from it by up to
+    ~5e-3 on [0,1] images, SURVEY.md section 7 "dtype contract"); ``exact=True`` reproduces the half loop bit for bit.
+    The two casts are plain torch element-wise copies around the kernel; fusing them into the kernel's staging and store
+    is listed as next work in DESIGN.md."""
+
+    def __init__(self, images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma):
+        self.images, self.tapset, self.psf_indices, self.outs = images, tapset, psf_indices, outs
+        self.kw = dict(noise=None if noise is None else [None if z is None else z.float() for z in noise], noise_sd=noise_sd,
+                       clamp=clamp, philox_seed=philox_seed, mean=mean, std=std, gamma=gamma, exact=False)
+
+    def run(self):
+        wide = [im.float() for im in self.images]
+        res32 = prepare_blur(wide, self.tapset, self.psf_indices, **self.kw).run()
+        results = []
+        for k, r in enumerate(res32):
+            if self.outs is not None and self.outs[k] is not None:
+                self.outs[k].copy_(r)
+                results.append(self.outs[k])
+            else:
+                results.append(r.to(torch.float16))
+        return results
 
 
 def blur_batch(images, tapset, psf_indices, **kwargs):

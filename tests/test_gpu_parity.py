@@ -315,3 +315,24 @@ def test_many_images_one_call(dib):
         dy, dx = k % 3, -(k % 4)
         H, W = imgs[k].shape[1:]
         assert torch.equal(outs[k][:, 8:H - 8, 8:W - 8], imgs[k][:, 8 - dy:H - 8 - dy, 8 - dx:W - 8 - dx]), k
+
+
+def test_half_images_fast_path_tolerance(dib, golden_dir):
+    """fp16 images, default path: fp32 accumulation rounded once; the reference's half loop rounds after every tap.
+    Stated tolerance 5e-3 against that loop; against the fp32 reference rounded to half it is 1 half-ulp."""
+    bf, ops = dib
+    g = _load(golden_dir, "blur_cases.npz")
+    worst = 0.0
+    for n in range(int(g["n"])):
+        img16 = _cuda(g["img_%d" % n], torch.float16)
+        psfn16 = _cuda(g["psfn_f16_%d" % n])
+        ref_half_loop = g["out_f16_%d" % n].astype(np.float64)
+        got = bf.manual_blur(img16, psfn16)                          # default: fast path
+        assert got.dtype == torch.float16 and tuple(got.shape) == g["out_f16_%d" % n].shape
+        err = np.abs(got.cpu().numpy().astype(np.float64) - ref_half_loop).max()
+        worst = max(worst, err)
+        assert err <= 5e-3, (n, err)
+        # the same taps applied in fp32 to the same (half-valued) image, rounded once, is what the fast path must give
+        want = bo.manual_blur(g["img_%d" % n].astype(np.float16).astype(np.float32), g["psfn_f16_%d" % n].astype(np.float32))
+        assert np.abs(got.cpu().numpy().astype(np.float64) - want.astype(np.float16).astype(np.float64)).max() <= 1e-3, n
+    assert worst > 0          # the two really are different computations
