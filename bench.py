@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -52,6 +52,11 @@ def workload_spec(name, batch):
         return dict(name="cfg2", batch=batch or 8, param_index=1, exposures=[0, 1, 2],
                     desc="gpu_blur of batch %dx3x800x1333 fp32, stored-format 128x128 PSFs, param_index 1 (expl 0.005), "
                          "low exposure (1/18, 1/10, 1/5)" % (batch or 8))
+    if name == "cfg5":
+        return dict(name="cfg5", batch=batch or 8, param_index=1, exposures=[0, 1, 2], fused_normalize=True,
+                    desc="fused blur->normalize of batch %dx3x800x1333 fp32 into the zero-padded %dx3x800x1344 batch that feeds "
+                         "GeneralizedRCNNTransform (canonical mean/std), stored-format PSFs, param_index 1, low exposure" % (
+                             batch or 8, batch or 8))
     return dict(name="cfg3", batch=batch or 16, param_index=3, exposures=[3, 4],
                 desc="gpu_blur of batch %dx3x800x1333 fp32, 128x128 PSFs, param_index 3 (expl 0.00005), "
                      "high exposure (1/2, 1)" % (batch or 16))
@@ -234,7 +239,10 @@ def run_own_arm(args, spec):
     gen = torch.Generator(device="cpu").manual_seed(1337 + rank)
     host_batches = [torch.rand((B, C, H, W), generator=gen).pin_memory() for _ in range(n_rot)]
     batches = [hb.to(dev) for hb in host_batches]
-    outs = torch.empty((B, C, H, W), device=dev)
+    fused = bool(spec.get("fused_normalize"))
+    outs = torch.zeros((B, C, H, 1344 if fused else W), device=dev)
+    out_views = [outs[i, :, :, :W] for i in range(B)]
+    norm_kw = dict(mean=[[0.485, 0.456, 0.406]] * B, std=[[0.229, 0.224, 0.225]] * B) if fused else {}
     traj, fracs = make_trajectories(spec, seed=1337 * rank)
     psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
     psfs = psfs16.float()                       # stored-format values (fp16 grid) in the image dtype
@@ -243,7 +251,7 @@ def run_own_arm(args, spec):
     taps = tapset.counts
     idx = list(range(B))
 
-    plans = [bf.prepare_blur([batches[r][i] for i in range(B)], tapset, idx, outs=[outs[i] for i in range(B)])
+    plans = [bf.prepare_blur([batches[r][i] for i in range(B)], tapset, idx, outs=out_views, **norm_kw)
              for r in range(n_rot)]
 
     def step(k):

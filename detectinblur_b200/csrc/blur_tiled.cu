@@ -518,19 +518,37 @@ __device__ __noinline__ void store_row_epilogue(const float* srow, float* g, con
 // k0 .. k1-1 lie wholly inside [0, wv) and go out as 16-byte stores; the <= 3 elements before the first and after the
 // last whole quad are stored one per lane.  (A specialised path for full-width rows with lane-dependent roles was
 // measured 4 % slower: the divergence costs more than the saved arithmetic.)
-__device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int skew, int wv, int lane) {
+template <bool kAffine>
+__device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int skew, int wv, int lane, float scale, float shift) {
     const int k0 = (skew + 3) >> 2, k1 = (wv + skew) >> 2;
     const int head = min(4 * k0 - skew, wv), tail0 = max(4 * k1 - skew, head);
 #pragma unroll
     for (int it = 0; it < (kWarpW + 3 + 127) / 128; ++it) {
         const int k = lane + 32 * it;
-        if (k >= k0 && k < k1) *reinterpret_cast<float4*>(g + (4 * k - skew)) = lds_v4(srow + 16u * (uint32_t)k);
+        if (k >= k0 && k < k1) {
+            float4 v = lds_v4(srow + 16u * (uint32_t)k);
+            if (kAffine) {
+                v.x = fmaf(v.x, scale, shift);
+                v.y = fmaf(v.y, scale, shift);
+                v.z = fmaf(v.z, scale, shift);
+                v.w = fmaf(v.w, scale, shift);
+            }
+            *reinterpret_cast<float4*>(g + (4 * k - skew)) = v;
+        }
     }
     const int x = lane < head ? lane : tail0 + (lane - head);
-    if (x < wv && (lane < head || x >= tail0)) g[x] = lds_f32(srow + 4u * (uint32_t)(skew + x));
+    if (x < wv && (lane < head || x >= tail0)) {
+        float v = lds_f32(srow + 4u * (uint32_t)(skew + x));
+        if (kAffine) v = fmaf(v, scale, shift);
+        g[x] = v;
+    }
 }
 
-template <bool kEpi>
+// Epilogue variants of the kernel: none; normalize only, applied as one FMA per pixel, x * (1/std) - mean/std (the
+// tiled kernel is not the bit-exact path, and an IEEE division per pixel would double its store cost); everything else.
+constexpr int kEpiNone = 0, kEpiAffine = 1, kEpiGeneral = 2;
+
+template <int kEpi>
 __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0,
                                            float2 (&acc)[kR][kCC], uint32_t obuf) {
     const int lane = threadIdx.x & 31;
@@ -541,6 +559,8 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
     ep.gamma = im.gamma;
     ep.mean = im.mean[ch & 3];
     ep.std = im.std[ch & 3];
+    const bool norm = (im.epilogue & DIB_EPI_NORMALIZE) != 0;
+    const float aff_scale = norm ? 1.0f / ep.std : 1.0f, aff_shift = norm ? -ep.mean / ep.std : 0.0f;
     float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
     const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
     uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
@@ -565,9 +585,9 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
         }
         __syncwarp();
         float* g1 = g + im.dst_rp;
-        if (!kEpi) {
-            if (r < nrows) store_row_plain(g, b0, skew0, wv, lane);
-            if (r + 1 < nrows) store_row_plain(g1, b1, skew1, wv, lane);
+        if (kEpi != kEpiGeneral) {
+            if (r < nrows) store_row_plain<kEpi == kEpiAffine>(g, b0, skew0, wv, lane, aff_scale, aff_shift);
+            if (r + 1 < nrows) store_row_plain<kEpi == kEpiAffine>(g1, b1, skew1, wv, lane, aff_scale, aff_shift);
         } else {
             const uint64_t stream = p.philox_offset + (uint64_t)im.philox_slot;
             const float* sm0 = reinterpret_cast<const float*>(__cvta_shared_to_generic(b0));
@@ -586,8 +606,8 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
 }
 
 // ---------------------------------------------------------------- kernel
-// kEpi selects the variant with the fused epilogue; batches without one run the leaner instantiation.
-template <bool kEpi>
+// kEpi selects the epilogue variant (kEpiNone / kEpiAffine / kEpiGeneral); batches without one run the leanest.
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
@@ -694,13 +714,14 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     DIB_CUDA(cudaGetDevice(&dev));
     if (attr_set_dev != dev) {
         DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set_dev = dev;
     }
     TiledParams p;
     int total = 0;
-    bool any_epi = false;
+    bool any_epi = false, any_general = false;
     for (int k = 0; k < n_sel; ++k) {   // `order` lists the images heaviest PSF first: tiles are handed out in this order
         const dib_image& im = images[order[k]];
         const dib_psf_meta& m = meta_host[im.psf_index];
@@ -722,6 +743,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.epilogue = im.epilogue;
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
         any_epi |= (t.epilogue != 0);
+        any_general |= (t.epilogue & ~DIB_EPI_NORMALIZE) != 0;
         t.philox_slot = order[k];
         t.noise_sd = im.noise_sd;
         t.gamma = im.gamma;
@@ -738,10 +760,12 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_offset = offset;
     p.sched = sched;
     const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
-    if (any_epi)
-        blur_tiled_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+    if (any_general)
+        blur_tiled_kernel<kEpiGeneral><<<grid, kThreads, kSmemBytes, st>>>(p);
+    else if (any_epi)
+        blur_tiled_kernel<kEpiAffine><<<grid, kThreads, kSmemBytes, st>>>(p);
     else
-        blur_tiled_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
+        blur_tiled_kernel<kEpiNone><<<grid, kThreads, kSmemBytes, st>>>(p);
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;
 }
