@@ -77,7 +77,7 @@ class BlurPlan(object):
 
 
 def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=None, clamp=None, philox_seed=None,
-                 mean=None, std=None, gamma=None, exact=None):
+                 mean=None, std=None, gamma=None, exact=None, pad_mode=None):
     """Build the descriptors of a batched blur of CHW CUDA tensors (same dtype, any sizes) with PSFs of ``tapset``.
 
     images       list of [C, H, W] tensors (float32 or float16, rows contiguous)
@@ -86,6 +86,8 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     noise        optional list of pre-drawn N(0,1) tensors (or None entries), ``noise_sd`` the matching sqrt(var)
     philox_seed  draw the noise in-kernel instead (Philox4x32-10); needs ``noise_sd``
     mean, std    optional per-image (C,) sequences: fused ``(x - mean) / std`` (net_transforms.py:135-139)
+    pad_mode     boundary mode for every image instead of manual_blur's own rule (``pad_mode_for``); the Fourier-path
+                 mirror (motion_blur/blur_image.py) asks for zeros outside the image at any size
     Returns a BlurPlan; ``plan.run()`` launches and returns the list of output tensors.
     """
     n = len(images)
@@ -93,7 +95,7 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     if n == 0:
         return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
     if images[0].dtype == torch.float16 and not exact:
-        return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma)
+        return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode)
     dev = images[0].device
     dtype = images[0].dtype
     if dtype not in _DT:
@@ -124,7 +126,10 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
         d.psf_index = int(psf_indices[k])
         d.src_row_pitch, d.src_chan_pitch = img.stride(1), img.stride(0)
         d.dst_row_pitch, d.dst_chan_pitch = out.stride(1), out.stride(0)
-        d.pad_mode = pad_mode_for(tapset.side, H, W) if d.psf_index >= 0 else _lib.PAD_REFLECT128
+        if pad_mode is not None:
+            d.pad_mode = int(pad_mode)
+        else:
+            d.pad_mode = pad_mode_for(tapset.side, H, W) if d.psf_index >= 0 else _lib.PAD_REFLECT128
         epi = 0
         if noise_sd is not None and noise_sd[k] is not None:
             nz = noise[k] if noise is not None else None
@@ -162,10 +167,10 @@ class _HalfPlan(object):
     The two casts are plain torch element-wise copies around the kernel; fusing them into the kernel's staging and store
     is listed as next work in DESIGN.md."""
 
-    def __init__(self, images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma):
+    def __init__(self, images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode=None):
         self.images, self.tapset, self.psf_indices, self.outs = images, tapset, psf_indices, outs
         self.kw = dict(noise=None if noise is None else [None if z is None else z.float() for z in noise], noise_sd=noise_sd,
-                       clamp=clamp, philox_seed=philox_seed, mean=mean, std=std, gamma=gamma, exact=False)
+                       clamp=clamp, philox_seed=philox_seed, mean=mean, std=std, gamma=gamma, exact=False, pad_mode=pad_mode)
 
     def run(self):
         wide = [im.float() for im in self.images]

@@ -11,9 +11,10 @@ What changed underneath:
     DataLoader workers must not touch CUDA, so there the transform only draws the trajectory and DEFERS rasterisation
     (``psf_backend="defer"``; blur_dict carries "trajectory"/"fraction" and psf=None); the main process completes the
     batch in one launch with ``complete_blur_dicts`` / ``upload_psfs`` (called by blur_image_list automatically);
-  * ``blur_image_in_transform=True`` (``--cpu_blur``) blurs with the same CUDA kernel as ``--gpu_blur`` instead of the CPU
-    Fourier path (motion_blur/blur_image.py), i.e. reflect borders and no per-image min-max contrast stretch; it needs
-    a CUDA-capable process and raises otherwise.  The Fourier path only survives as the timed CPU baseline (oracle/).
+  * ``blur_image_in_transform=True`` (``--cpu_blur``) keeps the Fourier path's semantics (edge padding, per-image
+    min-max contrast stretch, uint8 truncation; motion_blur/blur_image.py) but evaluates them as a tap sum on the CUDA
+    kernels (detectinblur_b200.motion_blur.BlurImageHandler); it needs a CUDA-capable process and raises otherwise.
+    The FFT implementation only survives as the timed CPU baseline (oracle/).
 """
 import math
 import random
@@ -151,7 +152,7 @@ class BlurImage(object):
             psf = psf / psf.max()
 
         output_image = image
-        if self.blur_image_in_transform:                                     # :344-359, on the GPU instead of CPU Fourier
+        if self.blur_image_in_transform:                                     # :344-359, the Fourier path's result on the GPU
             if psf is None:
                 raise RuntimeError("blur_image_in_transform=True needs a CUDA-capable process (psf_backend='cuda'); "
                                    "DataLoader workers cannot blur -- use --gpu_blur semantics (blur_image_in_transform=False)")
@@ -220,20 +221,13 @@ upload_psfs = complete_blur_dicts
 
 
 def blur_pil_image(image, psf, device=None):
-    """The ``--cpu_blur`` branch's job (transforms.py:349-359) done by the CUDA kernel: PIL RGB in, blurred uint8 PIL out."""
-    from PIL import Image
-    dev = torch.device(device) if device is not None else torch.device("cuda")
-    arr = np.asarray(image)
-    if arr.ndim == 2:
-        arr = np.stack([arr] * 3, axis=2)
-    t = torch.from_numpy(np.ascontiguousarray(arr.transpose(2, 0, 1))).to(dev).float() / 255.0
-    p = torch.as_tensor(np.asarray(psf, dtype=np.float32), device=dev)
-    if t.shape[1] == 64 or t.shape[2] == 64:
-        raise RuntimeError("a 64-px image side cannot be reflect-padded by 64 (the reference's GPU loop raises too)")
-    images = [t]
-    blur_functions.blur_image_list(images, [{"blurring": True}], [p])
-    out = (images[0].clamp(0, 1) * 255).to(torch.uint8).permute(1, 2, 0).contiguous().cpu().numpy()
-    return Image.fromarray(out)
+    """The ``--cpu_blur`` branch (transforms.py:349-359): PIL image in, blurred uint8 PIL image out, through the
+    BlurImageHandler mirror -- same borders, contrast stretch and truncation as the reference's Fourier path."""
+    from .motion_blur.blur_image import BlurImageHandler
+    handler = BlurImageHandler(image_path=None, PSFs=[np.asarray(psf).astype(np.float32)], pillowImage=image, device=device)
+    if not handler.blur_image():
+        print("Error in blurring.")
+    return handler.pilImageResult
 
 
 def add_jpeg_artifact_to_image(image_GPU, jpeg_compressor, quality):

@@ -80,19 +80,52 @@ def test_psf_class_mirror(cuda, golden_dir):
         assert bottom == max(0, ys.max() - 127) and top == max(0, 127 - ys.min())
 
 
+FOURIER_CASES = ("noise", "smooth", "odd", "odd2", "gray", "small", "olddelta")
+
+
+def test_blur_image_handler_matches_reference_fourier_path(cuda, golden_dir):
+    """motion_blur.BlurImageHandler (the --cpu_blur blur) on the CUDA kernels against the reference's own outputs:
+    even and odd sizes (the kernel origin moves to row 64), grey input, an image smaller than the kernel, oldDeltaPad.
+    Tolerances: 1e-5 on result[0], <= 1 level on the truncated uint8 image."""
+    from detectinblur_b200.motion_blur import BlurImageHandler
+    g = np.load(os.path.join(golden_dir, "fourier_cases.npz"), allow_pickle=False)
+    for name in FOURIER_CASES:
+        h = BlurImageHandler(None, PSFs=[g["psf"].copy()], pillowImage=Image.fromarray(g["in_" + name]))
+        assert h.blur_image(oldDeltaPad=(name == "olddelta")) is True
+        res, u8 = h.result[0], np.array(h.pilImageResult)
+        assert res.dtype == np.float32 and res.shape == g["res_" + name].shape, name
+        # the Lanczos resize of the upscaled case amplifies differences slightly
+        tol = 1e-5 if name != "small" else 2e-5
+        assert np.abs(res - g["res_" + name]).max() <= tol, (name, np.abs(res - g["res_" + name]).max())
+        assert u8.dtype == np.uint8 and u8.shape == g["u8_" + name].shape
+        assert np.abs(u8.astype(int) - g["u8_" + name].astype(int)).max() <= 1, name
+        assert (u8 != g["u8_" + name]).mean() < 5e-3, name
+
+
+def test_blur_image_handler_errors(cuda):
+    from detectinblur_b200.motion_blur import BlurImageHandler
+    with pytest.raises(Exception, match="Not correct path"):
+        BlurImageHandler("/nonexistent.png", PSFs=[np.zeros((128, 128), np.float32)])
+    with pytest.raises(AttributeError):
+        BlurImageHandler(None, PSFs=None, pillowImage=Image.new("RGB", (200, 200)))
+
+
 def test_cpu_blur_flag_blurs_on_the_gpu(cuda):
-    """blur_image_in_transform=True (--cpu_blur) returns a blurred uint8 PIL image produced by the CUDA kernel."""
+    """blur_image_in_transform=True (--cpu_blur): BlurImage returns the Fourier path's uint8 PIL image (edge padding,
+    min-max stretch), produced by the CUDA kernel; checked against the CPU restatement of blur_image.py."""
     from detectinblur_b200.transforms import BlurImage
-    arr = np.random.default_rng(1).integers(0, 256, (90, 120, 3), dtype=np.uint8)
+    from oracle import fourier_oracle as fo
+    arr = np.random.default_rng(1).integers(0, 256, (150, 171, 3), dtype=np.uint8)
     img = Image.fromarray(arr)
     random.seed(11)
     np.random.seed(11)
-    out, _, bd = BlurImage(prob=1.0, blur_type=0.005, blur_exposure=1 / 5, blur_image_in_transform=True, psf_backend="cuda")(img, None, {})
-    assert out.size == img.size and out.mode == "RGB"
-    psfn = bo.normalize_psf(bd["psf"].astype(np.float32))
-    want = bo.manual_blur(arr.transpose(2, 0, 1).astype(np.float32) / np.float32(255), psfn)
-    got = np.asarray(out).transpose(2, 0, 1).astype(np.float64) / 255
-    assert np.abs(got - np.clip(want, 0, 1)).max() <= 1.0 / 255 + 1e-6
+    tr = BlurImage(prob=1.0, blur_type=0.005, blur_exposure=1 / 5, blur_image_in_transform=True, psf_backend="cuda")
+    out, _, bd = tr(img, None, {})
+    assert out.size == img.size and out.mode == "RGB" and tr.pilImageResult is out
+    _, want = fo.fourier_blur(arr, bd["psf"].astype(np.float32))
+    got = np.asarray(out)
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+    assert (got != want).mean() < 5e-3
 
 
 def test_fused_blur_normalize_batch(cuda):

@@ -91,15 +91,33 @@ def test_trajectory_and_raster_bit_exact(golden_dir):
         assert abs(raw.sum() - po.time_weights(2000, frac).sum() / 2000) < 1e-9
 
 
+FOURIER_CASES = ("noise", "smooth", "odd", "odd2", "gray", "small", "olddelta")
+
+
+def _check_fourier(res, u8, g, name, tol):
+    assert res.shape == g["res_" + name].shape, name
+    assert np.abs(res - g["res_" + name]).max() <= tol, (name, np.abs(res - g["res_" + name]).max())
+    # uint8 truncation may flip on values within the tolerance of an integer boundary
+    assert (u8 != g["u8_" + name]).mean() < 2e-3, name
+    assert np.abs(u8.astype(int) - g["u8_" + name].astype(int)).max() <= 1, name
+
+
 def test_fourier_port(golden_dir):
+    """Even / odd sizes, grey input, an image smaller than the kernel (bicubic up, Lanczos back), oldDeltaPad."""
     g = _load(golden_dir, "fourier_cases.npz")
-    for name in ("noise", "smooth"):
-        res, u8 = fo.fourier_blur(g["in_" + name], g["psf"])
-        assert res.shape == g["res_" + name].shape
-        assert np.abs(res - g["res_" + name]).max() <= 2e-6, name
-        # uint8 truncation may flip on values within 2e-6 of an integer boundary
-        assert (u8 != g["u8_" + name]).mean() < 1e-3
-        assert np.abs(u8.astype(int) - g["u8_" + name].astype(int)).max() <= 1
+    for name in FOURIER_CASES:
+        res, u8 = fo.fourier_blur(g["in_" + name], g["psf"], old_delta_pad=(name == "olddelta"))
+        _check_fourier(res, u8, g, name, 2e-6)
+
+
+def test_fourier_as_tap_sum(golden_dir):
+    """The tap-sum form the CUDA path evaluates (zero-boundary convolution about kernel_centre) equals the FFT result."""
+    g = _load(golden_dir, "fourier_cases.npz")
+    for name in FOURIER_CASES:
+        res, u8 = fo.spatial_blur(g["in_" + name], g["psf"], old_delta_pad=(name == "olddelta"))
+        _check_fourier(res, u8, g, name, 1e-5)
+    assert fo.kernel_centre((128, 128), 288, 328) == (63, 63)
+    assert fo.kernel_centre((128, 128), 289, 331) == (64, 63)
 
 
 def test_normalize(golden_dir):

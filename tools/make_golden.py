@@ -236,17 +236,24 @@ def gen_fourier_case():
     # a smooth image as well: the min-max stretch depends on image contrast
     yy, xx = np.mgrid[0:160, 0:200]
     smooth = np.stack([40 + 150 * xx / 199, 60 + 100 * yy / 159, 90 + 60 * np.sin(xx / 17.0)], axis=2).astype(np.uint8)
+    # odd sizes move the zero-padded kernel's centre (blur_image.py:119-123); a 2-D image is replicated to RGB (:91-97);
+    # an image smaller than the kernel is upscaled first and scaled back afterwards (:56-69, :142-143)
+    odd = rng.integers(0, 256, (161, 203, 3), dtype=np.uint8)
+    odd2 = rng.integers(0, 256, (150, 131, 3), dtype=np.uint8)
+    gray = rng.integers(0, 256, (140, 150), dtype=np.uint8)
+    small = rng.integers(0, 256, (90, 100, 3), dtype=np.uint8)
     _, _, cen = ref_psf(0.005, 1 / 10, 1337)
     psf = cen[64:192, 64:192].astype(np.float32)
     cases = {"psf": psf}
-    for name, a in (("noise", arr), ("smooth", smooth)):
+    for name, a, kw in (("noise", arr, {}), ("smooth", smooth, {}), ("odd", odd, {}), ("odd2", odd2, {}), ("gray", gray, {}),
+                        ("small", small, {}), ("olddelta", rng.integers(0, 256, (171, 171, 3), dtype=np.uint8), {"oldDeltaPad": True})):
         h = BlurImageHandler(None, PSFs=[psf.copy()], pillowImage=Image.fromarray(a))
-        assert h.blur_image()
+        assert h.blur_image(**kw)
         cases["in_" + name] = a
         cases["res_" + name] = h.result[0]
         cases["u8_" + name] = np.array(h.pilImageResult)
     np.savez_compressed(os.path.join(OUT, "fourier_cases.npz"), **cases)
-    print("fourier cases: 2")
+    print("fourier cases: 7")
 
 
 def gen_normalize_case():
@@ -285,9 +292,8 @@ def gen_estimator_cases():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_psf_cases()
-    gen_blur_cases()
-    gen_transform_cases()
-    gen_fourier_case()
-    gen_normalize_case()
-    gen_estimator_cases()
+    gens = [gen_psf_cases, gen_blur_cases, gen_transform_cases, gen_fourier_case, gen_normalize_case, gen_estimator_cases]
+    only = sys.argv[1:]          # e.g. `python tools/make_golden.py gen_fourier_case` regenerates one fixture
+    for g in gens:
+        if not only or g.__name__ in only:
+            g()
