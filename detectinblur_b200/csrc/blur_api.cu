@@ -13,7 +13,8 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
 
 static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
     if (meta_host == nullptr || io_dtype != DIB_F32 || im.psf_index < 0) return false;
-    if (im.pad_mode != DIB_PAD_REFLECT128 || im.H <= 64 || im.W <= 64) return false;
+    // reflect-101 or zero padding about centre 63; tiny images (the reference's own zero-padding case) stay on the generic kernel
+    if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return false;
     const dib_psf_meta& m = meta_host[im.psf_index];
     if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return false;
     if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) return false;

@@ -92,6 +92,7 @@ struct TiledImage {
     int first_tile;       // tiles of the images before this one
     int psf_index, nchunks;
     int epilogue;
+    int zero_pad;         // DIB_PAD_ZERO128: pixels outside the image read as 0 instead of being mirrored
     int philox_slot;      // position in the caller's batch (Philox stream id)
     float noise_sd, gamma;
     float mean[4], std[4];
@@ -271,7 +272,9 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
 // Producer group (4 warps): issue every load of one stage.  Thread t owns staged row t: it places the row (skewed so
 // that the 16-byte-aligned interior of the in-image segment lands 16-byte aligned), moves that interior with one TMA
 // bulk copy and fetches the <= 3 + 3 unaligned end floats with 4-byte cp.async.  Tiles that reach past the left /
-// right image border then get their reflect-101 columns, each warp covering the rows its own lanes placed.
+// right image border then get their reflect-101 columns, each warp covering the rows its own lanes placed.  In
+// zero-padding mode rows and columns outside the image are stored as zeros instead (plain shared-memory stores, which
+// the thread's own arrive on the stage barrier publishes to the consumers).
 __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar, int pt) {
     const TiledImage& im = p.img[st.img];
     const int lane = pt & 31, pw = pt >> 5;
@@ -294,7 +297,11 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     uint32_t bytes = 0;
     const float* gp = plane;
     int ro = sr * kPitch;
-    if (sr < nrows) {
+    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
+    if (sr < nrows && zero_row) {
+        float* drow = sm.tile + ro - cl;
+        for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
+    } else if (sr < nrows) {
         const int srow = reflect101(rt + sr, im.H);
         gp = plane + (int64_t)srow * im.src_rp;
         int xa_al = cl, xb_al = cl;          // nothing inside the image: every column is mirrored
@@ -328,9 +335,14 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
             if (r2 >= nrows) break;
             const float* gp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gp), l));
             float* drow2 = sm.tile + __shfl_sync(0xffffffffu, ro, l) - cl;
+            const bool zr = __shfl_sync(0xffffffffu, (int)zero_row, l) != 0;      // that row is already all zeros
             for (int k = lane; k < nleft + nright; k += 32) {
                 const int col = k < nleft ? cl + k : xb1 + (k - nleft);
-                cp_async_4(drow2 + col, gp2 + reflect101(col, im.W));
+                if (im.zero_pad) {
+                    if (!zr) drow2[col] = 0.0f;
+                } else {
+                    cp_async_4(drow2 + col, gp2 + reflect101(col, im.W));
+                }
             }
         }
     }
@@ -741,6 +753,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.psf_index = im.psf_index;
         t.nchunks = m.prog_chunks;
         t.epilogue = im.epilogue;
+        t.zero_pad = (im.pad_mode == DIB_PAD_ZERO128);
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
         any_epi |= (t.epilogue != 0);
         any_general |= (t.epilogue & ~DIB_EPI_NORMALIZE) != 0;

@@ -93,11 +93,12 @@ def source_index(n, coord, branch, pad_mode):
     return s
 
 
-def manual_blur(image, psf, noise=None, noise_var=None):
+def manual_blur(image, psf, noise=None, noise_var=None, pad_mode=None):
     """blur_functions.py:11-74 on a CHW numpy image (float32 or float16); psf is already normalised.
 
     ``noise`` (same shape as the result) and ``noise_var`` restate :72-74 with the random draws supplied
-    by the caller: ``clamp(out + noise * sqrt(noise_var), 0, 1)``.
+    by the caller: ``clamp(out + noise * sqrt(noise_var), 0, 1)``.  ``pad_mode`` overrides the reference's own choice
+    of boundary (:55-58); the Fourier-path mirror uses zero padding at sizes where manual_blur itself would reflect.
     Returns a CxHxW array (HxW when C == 1, mirroring the ``.squeeze()`` at :69).
     """
     image = np.asarray(image)
@@ -105,7 +106,7 @@ def manual_blur(image, psf, noise=None, noise_var=None):
     C, H, W = image.shape
     psf = np.asarray(psf)
     branch = branch_of(psf.shape[0])
-    pad_mode = pad_mode_of(branch, H, W)
+    pad_mode = pad_mode_of(branch, H, W) if pad_mode is None else pad_mode
     ys, xs, ws = compact_taps(psf)
     dt = image.dtype.type
     out = np.zeros((C, H, W), dtype=image.dtype)

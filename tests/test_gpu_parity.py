@@ -143,6 +143,25 @@ def test_tiled_vs_oracle_seeded(dib, shape):
     assert np.abs(got.astype(np.float64) - want).max() <= TOL_FP32
 
 
+@pytest.mark.parametrize("shape", [(3, 200, 300), (1, 65, 449), (2, 130, 1000), (3, 289, 331)])
+def test_zero_padding_mode_both_kernels(dib, shape):
+    """Zero padding at any size (what the Fourier-path mirror asks for): exact-order kernel bit-exact, tiled within 1e-5."""
+    bf, ops = dib
+    from detectinblur_b200 import _lib
+    rng = np.random.default_rng(sum(shape) + 1)
+    img = rng.random(shape, dtype=np.float32)
+    np.random.seed(shape[2])
+    psf16, _ = po.stored_psf(0.001, 1 / 2, np.random)
+    psfn = bo.normalize_psf(po.crop128(psf16).astype(np.float32))
+    want = bo.manual_blur(img, psfn, pad_mode=bo.PAD_ZERO).reshape(shape)
+    ts = ops.compact_taps(_cuda(psfn), normalize=False)
+    got_exact = bf.blur_batch([_cuda(img)], ts, [0], pad_mode=_lib.PAD_ZERO128, exact=True)[0].cpu().numpy()
+    assert np.array_equal(got_exact, want)
+    got = bf.blur_batch([_cuda(img)], ts, [0], pad_mode=_lib.PAD_ZERO128, exact=False)[0].cpu().numpy()
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL_FP32
+    assert bf.launch_count() > 0
+
+
 def test_full_size_properties(dib):
     """BASELINE config sizes (3 x 800 x 1333): size-independent properties + tiled vs exact-order kernel on device."""
     bf, ops = dib
