@@ -64,7 +64,7 @@ class Image(ctypes.Structure):
 
 
 EXPORTS = ("dib_abi_version", "dib_last_error", "dib_device_info", "dib_tapset_layout_for", "dib_compact_taps",
-           "dib_blur_batch", "dib_rasterize_psf", "dib_checksum", "dib_fp32_probe")
+           "dib_blur_batch", "dib_rasterize_psf", "dib_unpack_psfs", "dib_checksum", "dib_fp32_probe")
 
 
 def _load():
@@ -82,6 +82,7 @@ def _load():
     lib.dib_blur_batch.argtypes = [ctypes.POINTER(Image), i32, vp, i32, i32, ctypes.POINTER(PsfMeta), i32, i32, u64, u64,
                                    ctypes.POINTER(i32), vp]
     lib.dib_rasterize_psf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.dib_unpack_psfs.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp]
     lib.dib_checksum.argtypes = [vp, i32, i64, vp, i32, vp]
     lib.dib_fp32_probe.argtypes = [i32, vp, ctypes.POINTER(u64), vp]
     for name in EXPORTS:

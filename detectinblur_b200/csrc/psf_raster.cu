@@ -14,6 +14,11 @@
 // the contributions the Python loop adds (same expression, no FMA contraction), so parallelism is across cells
 // only.  np.sum's pairwise tree (blocks of 128 with 8 strided partial sums, then a balanced binary tree) and the
 // row-major centroid accumulation are reproduced as well, because the centring offset is an int() truncation.
+//
+// Cost: a cell is touched by a handful of short runs of consecutive samples (the walk moves ~0.05 cells per sample),
+// so the samples are cut into blocks of 32 with a bounding box each and a thread only walks the blocks whose box
+// contains its cell -- the additions it performs, and their order, are unchanged.  The scratch canvas is written
+// inside the trajectory's bounding box only; everything outside is known to be zero and is never read or cleared.
 #include "dib_common.cuh"
 
 namespace dib {
@@ -56,15 +61,13 @@ rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__
     __shared__ int s_tlast;
     __shared__ double s_tree[512];
     __shared__ int s_off[2];
+    __shared__ short4 s_bb[4096 / 32];       // per block of 32 samples: rows [x, y], cols [z, w] its weighted samples touch
 
     const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double fraction = fractions[n];
     const double* tr = traj + (size_t)n * iters * 2;
     double* canvas_buf = scratch + (size_t)n * canvas * canvas;
     const int cells = canvas * canvas;
-
-    // 0. clear the scratch canvas
-    for (int i = tid; i < cells; i += kRasterThreads) canvas_buf[i] = 0.0;
 
     // 1. samples, base cells and time weights
     int ymin = 1 << 20, ymaxn = 1 << 20, xmin = 1 << 20, xmaxn = 1 << 20, tlast = 0;
@@ -108,6 +111,28 @@ rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__
     const int y0 = s_box[0], y1 = min(-s_box[1], canvas - 1), x0 = s_box[2], x1 = min(-s_box[3], canvas - 1);
     const int t_last = s_tlast;
     const bool empty = (y0 > y1) || (x0 > x1);
+    // 1b. bounding box of every block of 32 samples (weighted samples only: the others add an exact 0.0)
+    const int nblk = t_last / 32 + 1;
+    for (int k = warp; k < nblk; k += kRasterThreads / 32) {
+        const int t = 32 * k + lane;
+        int rlo = 1 << 14, rhin = 1 << 14, clo = 1 << 14, chin = 1 << 14;
+        if (t <= t_last && s_w[t] != 0.0) {
+            const short2 m = s_m[t];
+            rlo = m.x;
+            rhin = -(m.x + 1);
+            clo = m.y;
+            chin = -(m.y + 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rlo = min(rlo, __shfl_xor_sync(0xffffffffu, rlo, o));
+            rhin = min(rhin, __shfl_xor_sync(0xffffffffu, rhin, o));
+            clo = min(clo, __shfl_xor_sync(0xffffffffu, clo, o));
+            chin = min(chin, __shfl_xor_sync(0xffffffffu, chin, o));
+        }
+        if (lane == 0) s_bb[k] = make_short4((short)rlo, (short)(-rhin), (short)clo, (short)(-chin));   // empty block: lo > hi
+    }
+    __syncthreads();
 
     // 2. one thread per cell of the bounding box; contributions added in ascending sample order
     if (!empty) {
@@ -115,13 +140,18 @@ rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__
         for (int cidx = tid; cidx < bw * bh; cidx += kRasterThreads) {
             const int cy = y0 + cidx / bw, cx = x0 + cidx % bw;
             double acc = 0.0;
-            for (int t = 0; t <= t_last; ++t) {
-                const short2 m = s_m[t];
-                const int dy = cy - m.x, dx = cx - m.y;
-                if ((unsigned)dy <= 1u && (unsigned)dx <= 1u) {
-                    // t_proportion * triangle_fun_prod(re - col, im - row)   (generate_PSF.py:64-75)
-                    const double v = __dmul_rn(s_w[t], __dmul_rn(tri(__dsub_rn(s_re[t], (double)cx)), tri(__dsub_rn(s_im[t], (double)cy))));
-                    acc = __dadd_rn(acc, v);
+            for (int k = 0; k < nblk; ++k) {
+                const short4 bb = s_bb[k];
+                if (cy < bb.x || cy > bb.y || cx < bb.z || cx > bb.w) continue;
+                const int t1 = min(32 * k + 31, t_last);
+                for (int t = 32 * k; t <= t1; ++t) {
+                    const short2 m = s_m[t];
+                    const int dy = cy - m.x, dx = cx - m.y;
+                    if ((unsigned)dy <= 1u && (unsigned)dx <= 1u) {
+                        // t_proportion * triangle_fun_prod(re - col, im - row)   (generate_PSF.py:64-75)
+                        const double v = __dmul_rn(s_w[t], __dmul_rn(tri(__dsub_rn(s_re[t], (double)cx)), tri(__dsub_rn(s_im[t], (double)cy))));
+                        acc = __dadd_rn(acc, v);
+                    }
                 }
             }
             canvas_buf[cy * canvas + cx] = __ddiv_rn(acc, (double)iters);   // PSF / iters (:77)
@@ -138,16 +168,24 @@ rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__
         for (int base = 0; base < nblocks; base += 512) {
             const int nb = min(512, nblocks - base);
             for (int b = tid; b < nb; b += kRasterThreads) {
-                const double* a = canvas_buf + (size_t)(base + b) * 128;
-                double r[8];
+                const int e0 = (base + b) * 128;             // flattened index of the block's first element
+                double sum = 0.0;                            // a block that misses the bounding box sums zeros
+                if (e0 / canvas <= y1 && (e0 + 127) / canvas >= y0) {
+                    double r[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] = a[j];
-                for (int i = 8; i < 128; i += 8) {
+                    for (int j = 0; j < 8; ++j) r[j] = 0.0;
+                    for (int i = 0; i < 128; i += 8) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+                        for (int j = 0; j < 8; ++j) {
+                            const int e = e0 + i + j, yy = e / canvas, xx = e - yy * canvas;
+                            const double a = (yy >= y0 && yy <= y1 && xx >= x0 && xx <= x1) ? canvas_buf[e] : 0.0;
+                            r[j] = i == 0 ? a : __dadd_rn(r[j], a);
+                        }
+                    }
+                    sum = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                                    __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
                 }
-                s_tree[b] = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                                      __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                s_tree[b] = sum;
             }
             __syncthreads();
             for (int stride = 1; stride < nb; stride <<= 1) {
@@ -204,7 +242,8 @@ rasterize_psf_kernel(const double* __restrict__ traj, const double* __restrict__
     for (int i = tid; i < out_side * out_side; i += kRasterThreads) {
         const int yy = crop0 + i / out_side, xx = crop0 + i % out_side;
         const int sy = ((yy + oy) % canvas + canvas) % canvas, sx = ((xx + ox) % canvas + canvas) % canvas;
-        o[i] = cast_out<T>(canvas_buf[sy * canvas + sx]);
+        const bool inbox = !empty && sy >= y0 && sy <= y1 && sx >= x0 && sx <= x1;
+        o[i] = cast_out<T>(inbox ? canvas_buf[sy * canvas + sx] : 0.0);
     }
 }
 
@@ -223,6 +262,7 @@ extern "C" int dib_rasterize_psf(const double* traj, const double* fractions, in
     DIB_CHECK_ARG(out_dtype == DIB_F64 || out_dtype == DIB_F32 || out_dtype == DIB_F16, "dib_rasterize_psf: bad out_dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = (size_t)iters * (3 * sizeof(double) + sizeof(short2));
+    DIB_CHECK_ARG(smem <= 200 * 1024, "dib_rasterize_psf: %d samples do not fit in shared memory", iters);
     if (out_dtype == DIB_F64) {
         DIB_CUDA(cudaFuncSetAttribute(rasterize_psf_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rasterize_psf_kernel<double><<<n, kRasterThreads, smem, st>>>(traj, fractions, iters, canvas, center, out_side,

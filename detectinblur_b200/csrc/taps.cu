@@ -7,7 +7,9 @@
 //   non_zero_points[i, 0] - 63, psf_GPU[y, x] per tap       models/blur_functions.py:67   (2 syncs per tap)
 //   min/max of the nonzero coordinates                      utils.py:372-380 (expand_targets)
 //   first/second moments of the support                     transforms.py:366-376 (PSF PCA)
-// One CTA per PSF, one launch per batch.
+// One CTA per PSF, one launch per batch.  PSFs up to 129 x 129 are first staged in shared memory with independent
+// (unrolled) loads, so the three passes over the cells and the program builder pay one round of global latency
+// instead of one per loop iteration; larger canvases (the 256 branch) read global memory throughout.
 #include "dib_common.cuh"
 
 namespace dib {
@@ -100,7 +102,18 @@ __device__ inline void mask_range_first_last(const unsigned* m, int y0, int y1, 
     }
 }
 
-template <typename T>
+constexpr int kStageMaxCells = 129 * 129;      // staged PSFs: 66 564 B of dynamic shared memory
+
+// cell i of the PSF as float: from the shared-memory copy when staged, else from global memory
+template <typename T, bool kStaged>
+__device__ __forceinline__ float psf_cell(const T* psf, const float* staged, int64_t i) {
+    if constexpr (kStaged)
+        return staged[i];
+    else
+        return PsfNum<T>::load(psf, i);
+}
+
+template <typename T, bool kStaged>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
                     dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog, SchedWords* __restrict__ sched) {
@@ -125,10 +138,16 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const T* psf = psfs + (int64_t)n * psf_stride;
     const int cells = side * side;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ float sh_psf[];
+    if constexpr (kStaged) {
+#pragma unroll 16
+        for (int i = tid; i < cells; i += kCompactThreads) sh_psf[i] = PsfNum<T>::load(psf, i);
+        __syncthreads();
+    }
 
     // 1. psf.sum() (blur_functions.py:98)
     double part = 0.0;
-    for (int i = tid; i < cells; i += kCompactThreads) part += (double)PsfNum<T>::load(psf, i);
+    for (int i = tid; i < cells; i += kCompactThreads) part += (double)psf_cell<T, kStaged>(psf, sh_psf, i);
     const double total = block_sum_double(part, sh_d);
     const float s = PsfNum<T>::round_sum(total);
 
@@ -144,7 +163,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         const int i = base + lane;
         float v = 0.0f, w = 0.0f;
         if (i < slab_hi) {
-            v = PsfNum<T>::load(psf, i);
+            v = psf_cell<T, kStaged>(psf, sh_psf, i);
             w = normalize ? PsfNum<T>::normalized(v, s) : v;
         }
         const bool nz = (w != 0.0f);
@@ -178,7 +197,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         const int i = base + lane;
         float w = 0.0f;
         if (i < slab_hi) {
-            const float v = PsfNum<T>::load(psf, i);
+            const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
             w = normalize ? PsfNum<T>::normalized(v, s) : v;
         }
         const bool nz = (w != 0.0f);
@@ -235,7 +254,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             for (int e = 0; e < kGroupW; ++e) {
                 const int x = xmin + g * kGroupW + e;
                 if (x < side) {
-                    const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                    const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
                     const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
                     any |= (w != 0.0f);
                 }
@@ -350,7 +369,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                         const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
                         float w = 0.0f;
                         if (x < side) {
-                            const float v = PsfNum<T>::load(psf, (int64_t)y * side + x);
+                            const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
                             w = normalize ? PsfNum<T>::normalized(v, s) : v;
                         }
                         wout[(sg.woff + step) * kGroupW + e] = w;
@@ -407,12 +426,36 @@ extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int
     uint8_t* prog = base + L.prog_offset;
     SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool staged = side * side <= kStageMaxCells;
+    const size_t smem = staged ? (size_t)side * side * sizeof(float) : 0;
+    if (staged) {
+        static thread_local int attr_dev = -1;      // opt in to > 48 KB of dynamic shared memory once per device
+        int dev = 0;
+        DIB_CUDA(cudaGetDevice(&dev));
+        if (attr_dev != dev) {
+            DIB_CUDA(cudaFuncSetAttribute(compact_taps_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kStageMaxCells * (int)sizeof(float)));
+            DIB_CUDA(cudaFuncSetAttribute(compact_taps_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kStageMaxCells * (int)sizeof(float)));
+            attr_dev = dev;
+        }
+    }
     if (psf_dtype == DIB_F32) {
-        compact_taps_kernel<float><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const float*>(psfs), side, psf_stride,
-                                                                       normalize, meta, taps, max_taps, prog, sched);
+        const float* p = static_cast<const float*>(psfs);
+        if (staged)
+            compact_taps_kernel<float, true><<<n_psfs, kCompactThreads, smem, st>>>(p, side, psf_stride, normalize, meta, taps,
+                                                                                    max_taps, prog, sched);
+        else
+            compact_taps_kernel<float, false><<<n_psfs, kCompactThreads, 0, st>>>(p, side, psf_stride, normalize, meta, taps,
+                                                                                  max_taps, prog, sched);
     } else {
-        compact_taps_kernel<__half><<<n_psfs, kCompactThreads, 0, st>>>(static_cast<const __half*>(psfs), side, psf_stride,
-                                                                        normalize, meta, taps, max_taps, prog, sched);
+        const __half* p = static_cast<const __half*>(psfs);
+        if (staged)
+            compact_taps_kernel<__half, true><<<n_psfs, kCompactThreads, smem, st>>>(p, side, psf_stride, normalize, meta, taps,
+                                                                                     max_taps, prog, sched);
+        else
+            compact_taps_kernel<__half, false><<<n_psfs, kCompactThreads, 0, st>>>(p, side, psf_stride, normalize, meta, taps,
+                                                                                   max_taps, prog, sched);
     }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;

@@ -120,8 +120,13 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("detectinblur_b200: PSF rasterisation runs on a CUDA device (there is no CPU path)")
-    t_traj = torch.from_numpy(traj.view(np.float64).reshape(n, iters * 2)).to(device, non_blocking=False)
-    t_fr = torch.from_numpy(fr).to(device)
+    # one pinned staging buffer, one asynchronous upload: [trajectories | fractions] as float64
+    stage = torch.empty(n * iters * 2 + n, dtype=torch.float64).pin_memory()
+    host = stage.numpy()
+    host[:n * iters * 2] = traj.view(np.float64).reshape(-1)
+    host[n * iters * 2:] = fr
+    dev_in = stage.to(device, non_blocking=True)
+    t_traj, t_fr = dev_in[:n * iters * 2], dev_in[n * iters * 2:]
     out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
     offs = torch.empty((n, 2), dtype=torch.int32, device=device)
     scratch = torch.empty((n, canvas, canvas), dtype=torch.float64, device=device)
@@ -132,6 +137,34 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
                                               ctypes.c_void_p(scratch.data_ptr()), _stream_ptr(device)))
     if return_offsets:
         return out, offs
+    return out
+
+
+def unpack_psfs(packed_taps, offsets, device, crop_lo=64, out_side=128, dtype=torch.float16):
+    """Expand packed sparse PSFs (psf_bank pack words, one uint32 per tap) into dense [n, out_side, out_side] PSFs on
+    ``device``: what transforms.py:301-309 + engine.py:84 deliver, from one pinned upload of the taps only."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("detectinblur_b200: PSFs are unpacked on a CUDA device (there is no CPU path)")
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    packed_taps = np.ascontiguousarray(packed_taps, dtype=np.uint32)
+    n = len(offsets) - 1
+    if n <= 0 or offsets[0] != 0 or offsets[-1] != len(packed_taps) or np.any(np.diff(offsets) < 0):
+        raise ValueError("offsets must be n + 1 non-decreasing tap offsets covering packed_taps")
+    if dtype not in _TORCH_TO_DIB:
+        raise TypeError("unpack_psfs writes float16/32/64 PSFs")
+    # one staging buffer, one host-to-device copy: [offsets | taps] (an empty tap list still needs a valid pointer)
+    stage = torch.empty(8 * (n + 1) + 4 * max(len(packed_taps), 1), dtype=torch.uint8).pin_memory()
+    host = stage.numpy()
+    host[:8 * (n + 1)] = offsets.view(np.uint8)
+    host[8 * (n + 1):8 * (n + 1) + 4 * len(packed_taps)] = packed_taps.view(np.uint8)
+    dev_buf = stage.to(device, non_blocking=True)
+    out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib.dib_unpack_psfs(ctypes.c_void_p(dev_buf.data_ptr() + 8 * (n + 1)), ctypes.c_void_p(dev_buf.data_ptr()),
+                                            n, int(crop_lo), int(out_side), ctypes.c_void_p(out.data_ptr()),
+                                            _TORCH_TO_DIB[dtype], _stream_ptr(device)))
+    dev_buf.record_stream(torch.cuda.current_stream(device))
     return out
 
 

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import blur_functions
+from . import psf_bank
 from . import psf_ops
 from .motion_blur.generate_trajectory import Trajectory
 
@@ -126,11 +127,9 @@ class BlurImage(object):
             param_index = self.blur_type if self.blur_type is not None else random.choice([1, 2, 3])
             fraction_index = self.blur_exposure if self.blur_exposure is not None else self._draw_fraction_index(stored=True)
             psf_index = random.randint(0, 12000 - 1)
-            path = self.stored_psf_directory + "/P" + str(param_index) + "E" + str(fraction_index) + "/I" + "{:06d}".format(psf_index)
-            with open(path, 'rb') as f:
-                psf = np.load(f)
-            if psf.shape[0] > 128:
-                psf = psf[64:128 + 64, 64:128 + 64]
+            # the reference's file read + 128 crop (:301-309), served from a packed bank when one is present
+            psf = psf_bank.load_stored_psf(self.stored_psf_directory, param_index, fraction_index, psf_index)
+            blur_dict["stored_psf_source"] = (self.stored_psf_directory, param_index, fraction_index, psf_index)
         else:                                                                # :311-335
             trajectory = Trajectory(canvas=256, max_len=96, expl=param).fit().fit()   # two walks drawn, the second kept
             center = not self.dont_center_psf
@@ -209,6 +208,18 @@ def complete_blur_dicts(blur_dicts, device, dtype=torch.float16):
             bd["theta_rad"], bd["scale_factor_lambda1"], bd["scale_factor_lambda2"] = psf_principal_components(host[j])
             del bd["deferred_psf"]
             psfs[k] = dense[j].to(dtype)
+    # stored PSFs that a packed bank holds go up as taps only: one pinned copy for the batch, expanded on the device
+    by_dir = {}
+    for k, bd in enumerate(blur_dicts):
+        src = bd.get("stored_psf_source")
+        if psfs[k] is None and bd.get("blurring") and src is not None and np.asarray(bd["psf"]).shape == (128, 128):
+            bank = psf_bank.bank_for(src[0])
+            if bank.words(*src[1:]) is not None:
+                by_dir.setdefault(src[0], []).append(k)
+    for directory, members in by_dir.items():
+        dense = psf_bank.bank_for(directory).upload([blur_dicts[k]["stored_psf_source"][1:] for k in members], device, dtype=dtype)
+        for j, k in enumerate(members):
+            psfs[k] = dense[j]
     for k, bd in enumerate(blur_dicts):
         if psfs[k] is None and bd.get("blurring"):
             psfs[k] = torch.as_tensor(np.asarray(bd["psf"]), dtype=dtype, device=device)

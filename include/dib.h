@@ -167,6 +167,20 @@ DIB_API int dib_rasterize_psf(const double* traj, const double* fractions, int n
                       int out_side, void* out, int out_dtype, int32_t* offsets, double* scratch, void* stream);
 
 /*
+ * Device-side reader of the packed sparse PSF bank: expands stored taps into the dense PSFs the reference's reader
+ * yields.  Replaces, for a whole batch, transforms.py:301-309 (np.load of a 131 KB float16[256,256] file per image, then
+ * the [64:192, 64:192] crop) followed by engine.py:84 (torch.HalfTensor(blur_dict["psf"]).to(device), one dense
+ * upload per image): the caller uploads only the taps.
+ *   taps        device array of packed taps: y | x << 8 | (fp16 bits) << 16, coordinates on the bank's 256 x 256 canvas,
+ *               row-major nonzero order per PSF
+ *   offsets     device array of n + 1 tap offsets (PSF k owns taps[offsets[k] .. offsets[k+1]))
+ *   crop_lo     first canvas row / column of the crop (64 for the reference reader, 0 for the whole canvas)
+ *   out         n x out_side x out_side dense PSFs of out_dtype (zero filled here; fp16 values are copied bit for bit)
+ */
+DIB_API int dib_unpack_psfs(const uint32_t* taps, const int64_t* offsets, int n, int crop_lo, int out_side, void* out,
+                    int out_dtype, void* stream);
+
+/*
  * Order-independent 64-bit checksum of a buffer's raw element bits (for cross-shard verification; the
  * multi-GPU path all-gathers one value per rank, mirroring utils.all_gather, utils.py:536-576).
  * `out` is one uint64 in device memory; accumulate != 0 adds to its current value.

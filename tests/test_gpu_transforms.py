@@ -218,6 +218,52 @@ def test_estimator_mirror_and_bank_writer(cuda, golden_dir, tmp_path):
                 assert np.array_equal(psf_bank.load_stored_psf(dest + "psfs", p + 1, e, index), want[64:192, 64:192])
 
 
+def test_packed_bank_upload_and_writer(cuda, tmp_path):
+    """Packed sparse bank on the device: dib_unpack_psfs expands a batch's taps into the dense PSFs the reference uploads
+    one by one (engine.py:84); the packed writer stores the same PSFs as the dense writer; complete_blur_dicts uses it."""
+    import detectinblur_b200.psf_ops as ops
+    from detectinblur_b200 import psf_bank
+    from detectinblur_b200.transforms import complete_blur_dicts
+    dest = str(tmp_path) + "/"
+    psf_bank.generate_psf_bank(dest, worker_index=1, num_workers=2, total_num_psfs=6, device=cuda, dense=True, packed=True)
+    bank_dir = dest + "psfs"
+    bank = psf_bank.PackedPsfBank(bank_dir)
+    keys = [(p, e, i) for p in (1, 2, 3) for e in range(5) for i in (3, 4, 5)]
+    dense_files = []
+    for (p, e, i) in keys:
+        full = np.load(open(bank_dir + "/P%dE%d/I%06d" % (p, e, i), "rb"))
+        dense_files.append(full)
+        assert np.array_equal(bank.dense(p, e, i).view(np.uint16), full[64:192, 64:192].view(np.uint16))
+    want = np.stack([f[64:192, 64:192] for f in dense_files])
+    for dt in (torch.float16, torch.float32, torch.float64):
+        got = bank.upload(keys, cuda, dtype=dt)
+        assert got.dtype == dt and tuple(got.shape) == (len(keys), 128, 128)
+        assert torch.equal(got.cpu(), torch.from_numpy(want).to(dt))
+    # whole canvas (crop_lo 0) straight through the C entry point's wrapper
+    words = [np.asarray(bank.words(*k)) for k in keys[:4]]
+    offs = np.concatenate([[0], np.cumsum([len(w) for w in words])])
+    full = ops.unpack_psfs(np.concatenate(words), offs, cuda, crop_lo=0, out_side=256, dtype=torch.float16).cpu().numpy()
+    assert np.array_equal(full.view(np.uint16), np.stack(dense_files[:4]).view(np.uint16))
+    with pytest.raises(ValueError):
+        ops.unpack_psfs(np.concatenate(words), offs[:-1], cuda)
+    # the tap set built from the unpacked PSFs is the one built from the dense uploads
+    a = ops.compact_taps(bank.upload(keys[:6], cuda, dtype=torch.float32), normalize=True)
+    b = ops.compact_taps(torch.from_numpy(want[:6]).to(cuda).float(), normalize=True)
+    for k in range(6):
+        (ya, xa, wa), (yb, xb, wb) = a.taps(k), b.taps(k)
+        assert np.array_equal(ya, yb) and np.array_equal(xa, xb) and np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
+    # complete_blur_dicts sends stored PSFs up as taps (blur_dicts as BlurImage leaves them, tests/test_transforms_cpu.py)
+    dicts = [{"blurring": True, "psf": bank.dense(*k), "stored_psf_source": (bank_dir,) + k} for k in keys[:3]]
+    dicts.insert(1, {"blurring": False, "psf": [0]})
+    dicts.append({"blurring": True, "psf": want[7]})                        # no bank source: dense upload
+    psfs = complete_blur_dicts(dicts, cuda)
+    for bd, t in zip(dicts, psfs):
+        if bd["blurring"]:
+            assert t.dtype == torch.float16 and torch.equal(t.cpu(), torch.HalfTensor(bd["psf"]))
+        else:
+            assert tuple(t.shape) == (1,)
+
+
 def test_eval_sweep_shapes_tiled_vs_exact(cuda):
     """BASELINE config 4: P in {0.005, 0.001, 0.00005} x E in {1/25, 1/10, 1/5, 1/2, 1} (evaluate.py:299-300) on
     COCO-val-like shapes: rasterise on the GPU, blur with the tiled kernel, compare with the exact-order kernel."""

@@ -80,6 +80,82 @@ def test_blur_image_mirror_matches_reference(golden, bank):
             assert bd["theta_rad"] == theta and bd["scale_factor_lambda1"] == s1 and bd["scale_factor_lambda2"] == s2
 
 
+def test_packed_bank_reads_like_the_dense_files(golden, bank, tmp_path):
+    """The packed sparse bank: same arrays as the reference reader, from ~1 KB per PSF."""
+    import shutil
+    from detectinblur_b200 import psf_bank
+    from detectinblur_b200.transforms import BlurImage
+    packed_dir = str(tmp_path / "packed")
+    shutil.copytree(bank, packed_dir)
+    done = psf_bank.pack_psf_bank(packed_dir, remove_dense=True)
+    assert done and all(n >= 1 for n in done.values())
+    assert not [f for _, _, fs in os.walk(packed_dir) for f in fs if f.startswith("I")]      # only packs are left
+    dense_bytes = sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(bank) for f in fs)
+    pack_bytes = sum(os.path.getsize(os.path.join(r, f)) for r, _, fs in os.walk(packed_dir) for f in fs)
+    assert pack_bytes * 20 < dense_bytes
+    checked = 0
+    for name in golden["bank_names"]:
+        folder, fname = str(name).split("/")[-2:]
+        p, e, i = int(folder[1:folder.index("E")]), int(folder[folder.index("E") + 1:]), int(fname[1:])
+        want = psf_bank.load_stored_psf(bank, p, e, i)                 # dense file
+        got = psf_bank.load_stored_psf(packed_dir, p, e, i)            # pack
+        assert got.dtype == np.float16 and got.shape == (128, 128)
+        assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+        words = psf_bank.bank_for(packed_dir).words(p, e, i)
+        assert len(words) == np.count_nonzero(np.load(open(os.path.join(bank, folder, fname), "rb")))
+        checked += 1
+    assert checked >= 3
+    # the BlurImage mirror draws the same blur from the packed bank, RNG stream included
+    img = Image.fromarray(np.random.default_rng(3).integers(0, 256, (96, 112, 3), dtype=np.uint8))
+    seen = 0
+    for n in range(int(golden["n"])):
+        ci, seed = (int(v) for v in golden["cfg_%d" % n])
+        kw = dict(CONFIGS[ci])
+        if not kw.get("use_stored_psfs"):
+            continue
+        kw.update(blur_image_in_transform=False, stored_psf_directory=packed_dir)
+        random.seed(seed)
+        np.random.seed(seed)
+        _, _, bd = BlurImage(psf_backend="defer", **kw)(img, None, {})
+        assert random.random() == float(golden["next_random_%d" % n])
+        if bd["blurring"]:
+            shape = tuple(int(v) for v in golden["psf_shape_%d" % n])
+            ref = np.zeros(int(np.prod(shape)), dtype=np.float16)
+            ref[golden["psf_idx_%d" % n]] = golden["psf_val_%d" % n]
+            assert np.array_equal(bd["psf"], ref.reshape(shape))
+            assert bd["stored_psf_source"][0] == packed_dir
+            seen += 1
+    assert seen >= 1
+
+
+def test_pack_format_round_trip_and_worker_slices(tmp_path):
+    from detectinblur_b200 import psf_bank
+    rng = np.random.default_rng(5)
+    canv = []
+    for k in range(5):
+        c = np.zeros((256, 256), np.float16)
+        n = int(rng.integers(0, 40))
+        c[rng.integers(0, 256, n), rng.integers(0, 256, n)] = rng.random(n).astype(np.float16)
+        canv.append(c)
+    canv[2][:] = 0                                            # an empty PSF keeps its slot
+    canv[3][0, 0] = canv[3][255, 255] = np.float16(6e-8)       # corners and a subnormal survive
+    for c in canv:
+        assert np.array_equal(psf_bank.unpack_words(psf_bank.pack_words(c)).view(np.uint16), c.view(np.uint16))
+    d = str(tmp_path)
+    psf_bank.write_pack(os.path.join(d, "P1E0.w000.dibpack"), 0, canv[:2])
+    psf_bank.write_pack(os.path.join(d, "P1E0.w001.dibpack"), 2, canv[2:])
+    bank = psf_bank.PackedPsfBank(d)
+    for k, c in enumerate(canv):
+        assert np.array_equal(bank.dense(1, 0, k), c[64:192, 64:192])
+    assert bank.words(1, 0, 5) is None and bank.words(2, 0, 0) is None and bank.dense(1, 0, 7) is None
+    with pytest.raises(TypeError):
+        psf_bank.pack_words(np.zeros((256, 256), np.float32))
+    with open(os.path.join(d, "P2E0.dibpack"), "wb") as f:
+        f.write(b"not a pack at all, really not")
+    with pytest.raises(ValueError):
+        psf_bank.PackedPsfBank(d).words(2, 0, 0)
+
+
 def test_preblurred_passthrough():
     from detectinblur_b200.transforms import BlurImage
     img = Image.new("RGB", (80, 70))
