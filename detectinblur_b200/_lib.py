@@ -63,8 +63,21 @@ class Image(ctypes.Structure):
     ]
 
 
+class ResizeImage(ctypes.Structure):
+    _fields_ = [
+        ("src", ctypes.c_void_p), ("dst", ctypes.c_void_p),
+        ("C", ctypes.c_int32), ("in_h", ctypes.c_int32), ("in_w", ctypes.c_int32),
+        ("out_h", ctypes.c_int32), ("out_w", ctypes.c_int32),
+        ("pad_h", ctypes.c_int32), ("pad_w", ctypes.c_int32),
+        ("normalize", ctypes.c_int32),
+        ("src_row_pitch", ctypes.c_int64), ("src_chan_pitch", ctypes.c_int64),
+        ("dst_row_pitch", ctypes.c_int64), ("dst_chan_pitch", ctypes.c_int64),
+        ("mean", ctypes.c_float * 4), ("std", ctypes.c_float * 4),
+    ]
+
+
 EXPORTS = ("dib_abi_version", "dib_last_error", "dib_device_info", "dib_tapset_layout_for", "dib_compact_taps",
-           "dib_blur_batch", "dib_rasterize_psf", "dib_unpack_psfs", "dib_checksum", "dib_fp32_probe")
+           "dib_blur_batch", "dib_rasterize_psf", "dib_unpack_psfs", "dib_resize_batch", "dib_checksum", "dib_fp32_probe")
 
 
 def _load():
@@ -83,6 +96,7 @@ def _load():
                                    ctypes.POINTER(i32), vp]
     lib.dib_rasterize_psf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
     lib.dib_unpack_psfs.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.dib_resize_batch.argtypes = [ctypes.POINTER(ResizeImage), i32, i32, ctypes.POINTER(i32), vp]
     lib.dib_checksum.argtypes = [vp, i32, i64, vp, i32, vp]
     lib.dib_fp32_probe.argtypes = [i32, vp, ctypes.POINTER(u64), vp]
     for name in EXPORTS:

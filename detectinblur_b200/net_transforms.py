@@ -2,16 +2,23 @@
 
 ``GeneralizedRCNNTransform.forward`` (net_transforms.py:82-133) normalises every image with its own row of
 ``newMeans`` / ``newSTDs`` (``normalize`` :135-139), resizes (:151-175) and packs the list into one zero-padded batch
-whose sides are multiples of 32 (``batch_images`` :218-249).  Here the normalisation is the epilogue of the blur
-kernel and the result lands directly inside the padded batch tensor (``fused_blur_normalize``), so blurred pixels
-are written once; a model built with ``GeneralizedRCNNTransform(..., normalize_images=False)`` -- the hook the
-reference already has (:70-80, :112-118) -- then consumes the batch unchanged.  Resizing stays torch code and only
-runs when an image is not already at the requested scale (identity at 800x1333).
+whose sides are multiples of 32 (``batch_images`` :218-249).  Here
+
+  * for images already at the requested scale (800x1333) the normalisation is the epilogue of the blur kernel and the
+    result lands directly inside the padded batch tensor (``fused_blur_normalize``): blurred pixels are written once;
+  * for images that need resizing (native-size COCO images) one more kernel, ``dib_resize_batch``, does normalize +
+    bilinear resize + zero padding in a single pass over the batch (``resize_normalize_batch``), instead of the
+    reference's five passes; ``fused_blur_normalize(..., min_size=, max_size=)`` chains it after the blur.
+
+A model built with ``GeneralizedRCNNTransform(..., normalize_images=False)`` -- the hook the reference already has
+(:70-80, :112-118) -- consumes the batch unchanged (``forward`` passes an ``ImageList`` through).
 """
+import ctypes
 import math
 
 import torch
 
+from . import _lib
 from . import blur_functions
 from . import psf_ops
 
@@ -56,8 +63,73 @@ def padded_batch_shape(sizes, size_divisible=32):
     return hp, wp
 
 
+_launch_count = 0
+
+
+def launch_count():
+    """Kernels launched by this module (resize passes); the blur's own count is blur_functions.launch_count()."""
+    return _launch_count
+
+
+def resize_normalize_batch(images, min_size, max_size, means=None, stds=None, size_divisible=32):
+    """normalize + resize + batch_images (net_transforms.py:82-133, eval-mode resize) of CHW CUDA tensors in ONE pass.
+
+    images      list of [C, H, W] CUDA tensors (float32 or float16, any sizes, rows contiguous)
+    min_size    the short-side target: one number, or one per image (training draws it per image, :151-158)
+    means/stds  per-image (C,) sequences, or None to skip the normalisation (``normalize_images=False``)
+    Returns ImageList(tensors=[N, C, Hp, Wp], image_sizes=[(h, w), ...]) with every element of the batch written here.
+    """
+    global _launch_count
+    n = len(images)
+    if n == 0:
+        raise ValueError("empty image list")
+    dev, dtype = images[0].device, images[0].dtype
+    if dtype not in (torch.float32, torch.float16):
+        raise TypeError("resize_normalize_batch takes float32 or float16 images, got %s" % dtype)
+    srcs, sizes = [], []
+    for k, img in enumerate(images):
+        psf_ops._require_cuda(img, "image %d" % k)
+        if img.dim() != 3:
+            raise ValueError("images is expected to be a list of 3d tensors of shape [C, H, W], got {}".format(img.shape))
+        if img.dtype != dtype or img.device != dev or img.shape[0] != images[0].shape[0]:
+            raise TypeError("all images of a batch must share dtype, device and channel count")
+        if img.stride(2) != 1:
+            img = img.contiguous()
+        srcs.append(img)
+        h, w = int(img.shape[1]), int(img.shape[2])
+        scale = resize_scale(h, w, min_size[k] if isinstance(min_size, (list, tuple)) else min_size, max_size)
+        sizes.append((int(math.floor(float(h) * scale)), int(math.floor(float(w) * scale))))   # interpolate's output size
+    hp, wp = padded_batch_shape(sizes, size_divisible)
+    C = int(images[0].shape[0])
+    batch = torch.empty((n, C, hp, wp), dtype=dtype, device=dev)
+    launches = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        stream = psf_ops._stream_ptr(dev)
+        for lo in range(0, n, _lib.MAX_BATCH):
+            cnt = min(_lib.MAX_BATCH, n - lo)
+            descs = (_lib.ResizeImage * cnt)()
+            for j in range(cnt):
+                k = lo + j
+                d, img = descs[j], srcs[k]
+                d.src, d.dst = img.data_ptr(), batch[k].data_ptr()
+                d.C, d.in_h, d.in_w = C, int(img.shape[1]), int(img.shape[2])
+                d.out_h, d.out_w = sizes[k]
+                d.pad_h, d.pad_w = hp, wp
+                d.src_row_pitch, d.src_chan_pitch = img.stride(1), img.stride(0)
+                d.dst_row_pitch, d.dst_chan_pitch = batch.stride(2), batch.stride(1)
+                d.normalize = 0
+                if means is not None and means[k] is not None:
+                    d.normalize = 1
+                    for c in range(min(C, 4)):
+                        d.mean[c] = float(means[k][c])
+                        d.std[c] = float(stds[k][c])
+            _lib.check(_lib.lib.dib_resize_batch(descs, cnt, blur_functions._DT[dtype], ctypes.byref(launches), stream))
+            _launch_count += launches.value
+    return ImageList(batch, sizes)
+
+
 def fused_blur_normalize(images_GPU, blur_dicts, psfs_GPU, newMeans=None, newSTDs=None, image_mean=None, image_std=None,
-                         size_divisible=32, exact=None):
+                         size_divisible=32, exact=None, min_size=None, max_size=None):
     """blur_image_list + normalize + batch_images in one pass over the pixels.
 
     images_GPU   list of [3, H, W] CUDA tensors (float32), as handed to blur_image_list
@@ -65,6 +137,9 @@ def fused_blur_normalize(images_GPU, blur_dicts, psfs_GPU, newMeans=None, newSTD
     psfs_GPU     per image dense PSF (ignored where not blurring)
     newMeans / newSTDs   optional [N, 3] per-image statistics (utils.get_norm_params, utils.py:219-273); the
                  canonical ImageNet statistics otherwise
+    min_size / max_size  the transform's resize target (eval mode: the last of ``min_size``).  When every image is
+                 already at that scale -- or no target is given -- the blur kernel normalises and writes straight into
+                 the batch; otherwise the images are blurred at native size and ``resize_normalize_batch`` finishes.
     Returns ImageList(tensors=[N, 3, Hp, Wp] zero padded, image_sizes=[(H, W), ...]).
     """
     n = len(images_GPU)
@@ -74,8 +149,6 @@ def fused_blur_normalize(images_GPU, blur_dicts, psfs_GPU, newMeans=None, newSTD
     image_std = CANONICAL_STD if image_std is None else image_std
     dev, dtype = images_GPU[0].device, images_GPU[0].dtype
     sizes = [(int(im.shape[1]), int(im.shape[2])) for im in images_GPU]
-    hp, wp = padded_batch_shape(sizes, size_divisible)
-    batch = torch.zeros((n, int(images_GPU[0].shape[0]), hp, wp), dtype=dtype, device=dev)
     means = [list(newMeans[i]) if newMeans is not None else list(image_mean) for i in range(n)]
     stds = [list(newSTDs[i]) if newSTDs is not None else list(image_std) for i in range(n)]
     blurred = [k for k in range(n) if blur_dicts[k]["blurring"]]
@@ -91,6 +164,13 @@ def fused_blur_normalize(images_GPU, blur_dicts, psfs_GPU, newMeans=None, newSTD
         tapset = psf_ops.compact_taps(stack, normalize=True)
         for j, k in enumerate(blurred):
             idx[k] = j
+    if min_size is not None:
+        target = min_size[-1] if isinstance(min_size, (list, tuple)) else min_size
+        if any(resize_scale(h, w, target, max_size) != 1.0 for h, w in sizes):
+            blurred = blur_functions.blur_batch(list(images_GPU), tapset, idx, exact=exact) if tapset is not None else list(images_GPU)
+            return resize_normalize_batch(blurred, target, max_size, means, stds, size_divisible)
+    hp, wp = padded_batch_shape(sizes, size_divisible)
+    batch = torch.zeros((n, int(images_GPU[0].shape[0]), hp, wp), dtype=dtype, device=dev)
     outs = [batch[k, :, :sizes[k][0], :sizes[k][1]] for k in range(n)]
     blur_functions.blur_batch(list(images_GPU), tapset, idx, outs=outs, mean=means, std=stds, exact=exact)
     return ImageList(batch, sizes)
@@ -123,6 +203,24 @@ class GeneralizedRCNNTransform(torch.nn.Module):
         if isinstance(images, ImageList):
             return images, targets                   # already normalised and batched by fused_blur_normalize
         images = [img for img in images]
+        if images and all(img.is_cuda and img.dim() == 3 and img.dtype in (torch.float32, torch.float16) for img in images):
+            # CUDA tensors: normalize + resize + batch in one kernel pass.  Training draws the short-side target per image
+            # from torch's CPU generator exactly as torch_choice does (:141-149, :154-155), so seeded runs stay in step;
+            # target (box / mask / keypoint) resizing stays with the reference's own transform.
+            if targets is not None:
+                raise NotImplementedError("target resizing is the detector's side of the transform; pass targets=None here")
+            if self.training:
+                target_sizes = [float(self.min_size[int(torch.empty(1).uniform_(0., float(len(self.min_size))).item())])
+                                for _ in images]
+            else:
+                target_sizes = [float(self.min_size[-1])] * len(images)
+            means = stds = None
+            if self.normalize_images:
+                if newMeans is not None:
+                    means, stds = [newMeans[i, :] for i in range(len(images))], [newSTDs[i, :] for i in range(len(images))]
+                else:
+                    means, stds = [self.image_mean] * len(images), [self.image_std] * len(images)
+            return resize_normalize_batch(images, target_sizes, float(self.max_size), means, stds), targets
         for i in range(len(images)):
             image = images[i]
             if image.dim() != 3:
@@ -132,7 +230,11 @@ class GeneralizedRCNNTransform(torch.nn.Module):
                     image = self.normalize(image, newMeans[i, :], newSTDs[i, :])
                 else:
                     image = self.normalize(image, self.image_mean, self.image_std)
-            scale = resize_scale(image.shape[-2], image.shape[-1], self.min_size[-1], self.max_size)
+            if self.training:                        # torch_choice (:141-149)
+                size = float(self.min_size[int(torch.empty(1).uniform_(0., float(len(self.min_size))).item())])
+            else:
+                size = float(self.min_size[-1])
+            scale = resize_scale(image.shape[-2], image.shape[-1], size, self.max_size)
             if scale != 1.0:
                 image = torch.nn.functional.interpolate(image[None], scale_factor=scale, mode='bilinear',
                                                         recompute_scale_factor=True, align_corners=False)[0]

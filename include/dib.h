@@ -167,6 +167,27 @@ DIB_API int dib_rasterize_psf(const double* traj, const double* fractions, int n
                       int out_side, void* out, int out_dtype, int32_t* offsets, double* scratch, void* stream);
 
 /*
+ * One image of a fused normalize + bilinear resize + zero-padded batch pass (dib_resize_batch).
+ */
+typedef struct dib_resize_image {
+    const void* src;          /* C x in_h x in_w source (the blurred image), rows contiguous */
+    void* dst;                /* this image's C planes inside the padded batch tensor */
+    int32_t C, in_h, in_w;
+    int32_t out_h, out_w;     /* resized extent, floor(in * scale_factor) as torch computes it */
+    int32_t pad_h, pad_w;     /* extent of the destination plane to fill: zeros outside out_h x out_w */
+    int32_t normalize;        /* != 0: (x - mean[c]) / std[c] */
+    int64_t src_row_pitch, src_chan_pitch, dst_row_pitch, dst_chan_pitch;    /* in elements */
+    float mean[4], std[4];
+} dib_resize_image;
+
+/*
+ * Normalize, resize (bilinear, align_corners=False, recomputed scale) and batch up to DIB_MAX_BATCH images in one
+ * pass.  Replaces GeneralizedRCNNTransform.forward's per-image normalize (models/net_transforms.py:135-139), resize
+ * (:36-48, :151-175) and batch_images (:218-249).  *launches (optional) receives the number of kernels launched.
+ */
+DIB_API int dib_resize_batch(const dib_resize_image* images, int n_images, int io_dtype, int* launches, void* stream);
+
+/*
  * Device-side reader of the packed sparse PSF bank: expands stored taps into the dense PSFs the reference's reader
  * yields.  Replaces, for a whole batch, transforms.py:301-309 (np.load of a 131 KB float16[256,256] file per image, then
  * the [64:192, 64:192] crop) followed by engine.py:84 (torch.HalfTensor(blur_dict["psf"]).to(device), one dense

@@ -31,12 +31,13 @@ def test_header_is_plain_c_and_struct_sizes_match(tmp_path):
     from detectinblur_b200 import _lib
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "dib.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(dib_tap), '
-                   'sizeof(dib_psf_meta), sizeof(dib_image), sizeof(dib_tapset_layout));return 0;}\n')
+                   'sizeof(dib_psf_meta), sizeof(dib_image), sizeof(dib_tapset_layout));'
+                   'printf("%zu\\n", sizeof(dib_resize_image));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [ctypes.sizeof(_lib.Tap), ctypes.sizeof(_lib.PsfMeta), ctypes.sizeof(_lib.Image),
-                     ctypes.sizeof(_lib.TapsetLayout)]
+                     ctypes.sizeof(_lib.TapsetLayout), ctypes.sizeof(_lib.ResizeImage)]
 
 
 def test_argument_validation_without_a_gpu():
@@ -52,6 +53,12 @@ def test_argument_validation_without_a_gpu():
     assert rc == _lib.ERR_INVALID and b"n_images" in _lib.lib.dib_last_error()
     rc = _lib.lib.dib_blur_batch(img, 1, None, 0, 0, None, 0, 0, 0, 0, None, None)
     assert rc == _lib.ERR_INVALID and b"NULL" in _lib.lib.dib_last_error()
+    rz = (_lib.ResizeImage * 1)()
+    assert _lib.lib.dib_resize_batch(rz, 0, 0, None, None) == _lib.ERR_INVALID and b"n_images" in _lib.lib.dib_last_error()
+    assert _lib.lib.dib_resize_batch(rz, 1, 0, None, None) == _lib.ERR_INVALID and b"NULL" in _lib.lib.dib_last_error()
+    assert _lib.lib.dib_unpack_psfs(None, None, 1, 64, 128, None, 1, None) == _lib.ERR_INVALID
+    assert _lib.lib.dib_unpack_psfs(ctypes.c_void_p(8), ctypes.c_void_p(8), 1, 200, 128, ctypes.c_void_p(8), 1, None) == _lib.ERR_INVALID
+    assert b"canvas" in _lib.lib.dib_last_error()
     rc = _lib.lib.dib_compact_taps(None, 0, 1, 128, 128 * 128, 1, None, 1024, None)
     assert rc == _lib.ERR_INVALID
     rc = _lib.lib.dib_rasterize_psf(ctypes.c_void_p(8), ctypes.c_void_p(8), 1, 2000, 200, 1, 128, ctypes.c_void_p(8), 1, None,

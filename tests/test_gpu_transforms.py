@@ -218,6 +218,62 @@ def test_estimator_mirror_and_bank_writer(cuda, golden_dir, tmp_path):
                 assert np.array_equal(psf_bank.load_stored_psf(dest + "psfs", p + 1, e, index), want[64:192, 64:192])
 
 
+def test_resize_normalize_batch_matches_reference_transform(cuda, golden_dir):
+    """dib_resize_batch (normalize + bilinear resize + zero-padded batch in one pass) against the reference's
+    GeneralizedRCNNTransform.forward outputs; tolerance 5e-6 on normalised values (|x| <= 2.7; FMA contraction)."""
+    from detectinblur_b200 import net_transforms as nt
+    g = np.load(os.path.join(golden_dir, "resize_cases.npz"), allow_pickle=False)
+    for n in range(int(g["n"])):
+        mn, mx = (float(v) for v in g["minmax_%d" % n])
+        imgs = [torch.from_numpy(g["img_%d_%d" % (n, k)]).to(cuda) for k in range(int(g["n_img_%d" % n]))]
+        tr = nt.GeneralizedRCNNTransform(mn, mx, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225], training=False)
+        before = nt.launch_count()
+        il, _ = tr(imgs, None, newMeans=g["means_%d" % n], newSTDs=g["stds_%d" % n])
+        assert nt.launch_count() == before + 1                       # one kernel for the whole batch
+        assert [list(s) for s in il.image_sizes] == g["sizes_%d" % n].tolist()
+        got, want = il.tensors.cpu().numpy(), g["batch_%d" % n]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 5e-6, (n, np.abs(got - want).max())
+        # the padding is written by the kernel (the batch starts as torch.empty): exact zeros outside every image
+        for k, (h, w) in enumerate(il.image_sizes):
+            assert not got[k, :, h:, :].any() and not got[k, :, :, w:].any()
+        # half I/O and no normalisation
+        il16, _ = nt.GeneralizedRCNNTransform(mn, mx, None, None, training=False, normalize_images=False)([i.half() for i in imgs])
+        ref = nt.GeneralizedRCNNTransform(mn, mx, None, None, training=False, normalize_images=False)([i.half().float().cpu() for i in imgs])[0]
+        assert il16.tensors.dtype == torch.float16
+        assert np.abs(il16.tensors.float().cpu().numpy() - ref.tensors.numpy()).max() <= 1e-3
+
+
+def test_fused_blur_normalize_with_resize(cuda):
+    """blur at native size, then normalize + resize + batch: against oracle blur -> oracle transform."""
+    from detectinblur_b200 import net_transforms as nt
+    from oracle import resize_oracle as ro
+    rng = np.random.default_rng(12)
+    shapes = [(3, 97, 131), (3, 120, 100), (3, 70, 140)]
+    imgs = [rng.random(s, dtype=np.float32) for s in shapes]
+    np.random.seed(12)
+    psfs = []
+    for frac in (1 / 10, 1 / 5, 1 / 18):
+        p16, _ = po.stored_psf(0.005, frac, np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    blur_dicts = [{"blurring": True}, {"blurring": False}, {"blurring": True}]
+    means = np.array([[0.47, 0.45, 0.41], nt.CANONICAL_MEAN, [0.5, 0.4, 0.3]])
+    stds = np.array([[0.21, 0.2, 0.22], nt.CANONICAL_STD, [0.25, 0.2, 0.3]])
+    il = nt.fused_blur_normalize([torch.from_numpy(i).to(cuda) for i in imgs], blur_dicts,
+                                 [torch.from_numpy(p).to(cuda) for p in psfs], newMeans=means, newSTDs=stds,
+                                 min_size=160, max_size=200)
+    blurred = [bo.manual_blur(imgs[k], bo.normalize_psf(psfs[k])) if blur_dicts[k]["blurring"] else imgs[k] for k in range(3)]
+    want, sizes = ro.transform_forward(blurred, means, stds, 160, 200)
+    assert [tuple(s) for s in il.image_sizes] == sizes
+    got = il.tensors.cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-5            # tiled blur (<= 1e-5 on [0,1]) scaled by 1/std ~ 5, plus the resize
+    # at the requested scale already: the one-kernel path (blur epilogue writes the batch)
+    same = nt.fused_blur_normalize([torch.from_numpy(imgs[0]).to(cuda)], [blur_dicts[0]], [torch.from_numpy(psfs[0]).to(cuda)],
+                                   newMeans=means[:1], newSTDs=stds[:1], min_size=97, max_size=131)
+    assert same.image_sizes == [(97, 131)]
+
+
 def test_packed_bank_upload_and_writer(cuda, tmp_path):
     """Packed sparse bank on the device: dib_unpack_psfs expands a batch's taps into the dense PSFs the reference uploads
     one by one (engine.py:84); the packed writer stores the same PSFs as the dense writer; complete_blur_dicts uses it."""

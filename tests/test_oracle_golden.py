@@ -120,6 +120,20 @@ def test_fourier_as_tap_sum(golden_dir):
     assert fo.kernel_centre((128, 128), 289, 331) == (64, 63)
 
 
+def test_transform_resize_port(golden_dir):
+    """normalize + bilinear resize + zero-padded batch (net_transforms.py:82-133) against the reference's own outputs."""
+    from oracle import resize_oracle as ro
+    g = _load(golden_dir, "resize_cases.npz")
+    for n in range(int(g["n"])):
+        mn, mx = (float(v) for v in g["minmax_%d" % n])
+        imgs = [g["img_%d_%d" % (n, k)] for k in range(int(g["n_img_%d" % n]))]
+        batch, sizes = ro.transform_forward(imgs, g["means_%d" % n], g["stds_%d" % n], mn, mx)
+        assert [list(s) for s in sizes] == g["sizes_%d" % n].tolist()
+        assert batch.shape == g["batch_%d" % n].shape
+        # torch contracts the interpolation's multiply-adds; the restatement rounds each product: <= 2 ulp of |x| <= 2.7
+        assert np.abs(batch - g["batch_%d" % n]).max() <= 1e-6, n
+
+
 def test_normalize(golden_dir):
     g = _load(golden_dir, "normalize_case.npz")
     assert np.array_equal(bo.normalize_image(g["img"], g["mean"], g["std"]), g["out"])

@@ -96,6 +96,30 @@ def main():
         return ops.rasterize_psfs(big, bigf, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
 
     rdev, rwall = timed(raster, 10)
+    # the input transform after the blur: normalize + resize to 800 / 1333 + zero-padded batch, 8 COCO-size images
+    from detectinblur_b200 import net_transforms as nt
+    timgs = [images[k] for k in range(8)]
+    means = [nt.CANONICAL_MEAN] * 8
+    stds = [nt.CANONICAL_STD] * 8
+    fused_us, _ = timed(lambda: nt.resize_normalize_batch(timgs, 800.0, 1333.0, means, stds), args.repeats)
+    il = nt.resize_normalize_batch(timgs, 800.0, 1333.0, means, stds)
+
+    def torch_ops():       # the reference's own sequence of torch calls (net_transforms.py:112-133) on the same device
+        outs = []
+        for im in timgs:
+            x = nt.normalize(im, nt.CANONICAL_MEAN, nt.CANONICAL_STD)
+            sc = nt.resize_scale(im.shape[1], im.shape[2], 800.0, 1333.0)
+            outs.append(torch.nn.functional.interpolate(x[None], scale_factor=sc, mode="bilinear", recompute_scale_factor=True,
+                                                        align_corners=False)[0])
+        hp, wp = nt.padded_batch_shape([(int(o.shape[1]), int(o.shape[2])) for o in outs])
+        batch = outs[0].new_full((len(outs), 3, hp, wp), 0)
+        for o, pad in zip(outs, batch):
+            pad[:, :o.shape[1], :o.shape[2]].copy_(o)
+        return batch
+
+    torch_us, _ = timed(torch_ops, args.repeats)
+    tdiff = float((torch_ops() - il.tensors).abs().max())
+    tbytes = sum(im.numel() * 4 for im in timgs) + il.tensors.numel() * 4
     b1_dev = sum(c["device_us"] for c in per_cell)
     b1_wall = sum(c["wall_us"] for c in per_cell)
     print(json.dumps({
@@ -106,7 +130,10 @@ def main():
                       "images_per_s_wall": n / (bwall * 1e-6)},
         "rasterizer_batch256": {"device_us": rdev, "wall_us_incl_h2d": rwall, "psfs_per_s_device": 256 / (rdev * 1e-6),
                                 "psfs_per_s_wall": 256 / (rwall * 1e-6)},
-        "gpu_launches": bf.launch_count() - l0,
+        "transform_8_images": {"batch_shape": list(il.tensors.shape), "fused_kernel_us": fused_us, "torch_ops_us": torch_us,
+                               "algorithmic_bytes": tbytes, "fused_gbs": tbytes / (fused_us * 1e-6) / 1e9,
+                               "max_abs_diff_vs_torch_cuda": tdiff},
+        "gpu_launches": bf.launch_count() - l0 + nt.launch_count(),
         "reference_cost_note": "the reference spends ~18 ms (trajectory) + ~45 ms (PSF splat loop) + O(taps) ATen launches per image",
     }))
 

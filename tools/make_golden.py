@@ -268,6 +268,34 @@ def gen_normalize_case():
     print("normalize case: 1")
 
 
+def gen_resize_cases():
+    """GeneralizedRCNNTransform.forward in eval mode (normalize with per-image statistics, bilinear resize, zero-padded
+    batch; net_transforms.py:82-133) on small COCO-shaped images: up- and down-scaling, landscape and portrait."""
+    from models.net_transforms import GeneralizedRCNNTransform
+    rng = np.random.default_rng(21)
+    cases = {}
+    specs = [((100, 140), [(3, 60, 80), (3, 80, 60), (3, 47, 83)]),       # upscale, max_size binds for the third
+             ((64, 96), [(3, 120, 161), (3, 97, 75)]),                      # downscale
+             ((90, 120), [(3, 90, 120), (3, 90, 101)])]                     # identity scale and a near-identity one
+    for n, ((mn, mx), shapes) in enumerate(specs):
+        tr = GeneralizedRCNNTransform(mn, mx, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225], training=False)
+        imgs = [rng.random(s, dtype=np.float32) for s in shapes]
+        means = np.stack([np.array([0.485, 0.456, 0.406]) + 0.02 * rng.standard_normal(3) for _ in shapes])
+        stds = np.stack([np.array([0.229, 0.224, 0.225]) * (1 + 0.1 * rng.random(3)) for _ in shapes])
+        il, _ = tr([torch.from_numpy(i) for i in imgs], None, newMeans=means, newSTDs=stds)
+        cases["minmax_%d" % n] = np.array([mn, mx])
+        cases["n_img_%d" % n] = len(shapes)
+        for k, im in enumerate(imgs):
+            cases["img_%d_%d" % (n, k)] = im
+        cases["means_%d" % n] = means
+        cases["stds_%d" % n] = stds
+        cases["batch_%d" % n] = il.tensors.numpy()
+        cases["sizes_%d" % n] = np.array(il.image_sizes)
+    cases["n"] = len(specs)
+    np.savez_compressed(os.path.join(OUT, "resize_cases.npz"), **cases)
+    print("resize cases: %d" % len(specs))
+
+
 def gen_estimator_cases():
     """engine_blur_estimator.manual_blur with resize_images (:27-70).  The module itself cannot be imported here (it pulls in
     pycocotools), so the two function definitions are executed from the reference file at run time; nothing is copied."""
@@ -292,7 +320,7 @@ def gen_estimator_cases():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gens = [gen_psf_cases, gen_blur_cases, gen_transform_cases, gen_fourier_case, gen_normalize_case, gen_estimator_cases]
+    gens = [gen_psf_cases, gen_blur_cases, gen_transform_cases, gen_fourier_case, gen_normalize_case, gen_resize_cases, gen_estimator_cases]
     only = sys.argv[1:]          # e.g. `python tools/make_golden.py gen_fourier_case` regenerates one fixture
     for g in gens:
         if not only or g.__name__ in only:
