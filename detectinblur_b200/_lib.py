@@ -77,7 +77,7 @@ class ResizeImage(ctypes.Structure):
 
 
 EXPORTS = ("dib_abi_version", "dib_last_error", "dib_device_info", "dib_tapset_layout_for", "dib_compact_taps",
-           "dib_blur_batch", "dib_rasterize_psf", "dib_unpack_psfs", "dib_resize_batch", "dib_checksum", "dib_fp32_probe")
+           "dib_blur_batch", "dib_rasterize_psf", "dib_generate_trajectories", "dib_unpack_psfs", "dib_resize_batch", "dib_checksum", "dib_fp32_probe")
 
 
 def _load():
@@ -95,6 +95,7 @@ def _load():
     lib.dib_blur_batch.argtypes = [ctypes.POINTER(Image), i32, vp, i32, i32, ctypes.POINTER(PsfMeta), i32, i32, u64, u64,
                                    ctypes.POINTER(i32), vp]
     lib.dib_rasterize_psf.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.dib_generate_trajectories.argtypes = [u64, u64, vp, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp]
     lib.dib_unpack_psfs.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp]
     lib.dib_resize_batch.argtypes = [ctypes.POINTER(ResizeImage), i32, i32, ctypes.POINTER(i32), vp]
     lib.dib_checksum.argtypes = [vp, i32, i64, vp, i32, vp]

@@ -112,21 +112,32 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
 
     Bit-identical to ``PSF(canvas, trajectory, [fraction]).fit()`` (+ ``centerPSF()`` + central crop + cast).
     """
-    traj = np.ascontiguousarray(np.asarray(trajectories, dtype=np.complex128))
-    if traj.ndim == 1:
-        traj = traj[None]
-    n, iters = traj.shape
-    fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("detectinblur_b200: PSF rasterisation runs on a CUDA device (there is no CPU path)")
-    # one pinned staging buffer, one asynchronous upload: [trajectories | fractions] as float64
-    stage = torch.empty(n * iters * 2 + n, dtype=torch.float64).pin_memory()
-    host = stage.numpy()
-    host[:n * iters * 2] = traj.view(np.float64).reshape(-1)
-    host[n * iters * 2:] = fr
-    dev_in = stage.to(device, non_blocking=True)
-    t_traj, t_fr = dev_in[:n * iters * 2], dev_in[n * iters * 2:]
+    if isinstance(trajectories, torch.Tensor):
+        # trajectories already on the device (generate_trajectories): no staging
+        if trajectories.dtype != torch.complex128 or not trajectories.is_cuda:
+            raise TypeError("device trajectories must be a complex128 CUDA tensor")
+        t = trajectories if trajectories.dim() == 2 else trajectories[None]
+        t = t.contiguous()
+        n, iters = int(t.shape[0]), int(t.shape[1])
+        t_traj = torch.view_as_real(t).reshape(-1)
+        fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
+        t_fr = torch.as_tensor(fr, device=device)
+    else:
+        traj = np.ascontiguousarray(np.asarray(trajectories, dtype=np.complex128))
+        if traj.ndim == 1:
+            traj = traj[None]
+        n, iters = traj.shape
+        fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
+        # one pinned staging buffer, one asynchronous upload: [trajectories | fractions] as float64
+        stage = torch.empty(n * iters * 2 + n, dtype=torch.float64).pin_memory()
+        host = stage.numpy()
+        host[:n * iters * 2] = traj.view(np.float64).reshape(-1)
+        host[n * iters * 2:] = fr
+        dev_in = stage.to(device, non_blocking=True)
+        t_traj, t_fr = dev_in[:n * iters * 2], dev_in[n * iters * 2:]
     out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
     offs = torch.empty((n, 2), dtype=torch.int32, device=device)
     scratch = torch.empty((n, canvas, canvas), dtype=torch.float64, device=device)
@@ -137,6 +148,34 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
                                               ctypes.c_void_p(scratch.data_ptr()), _stream_ptr(device)))
     if return_offsets:
         return out, offs
+    return out
+
+
+def generate_trajectories(n, expl, seed, device, first_index=0, canvas=256, iters=2000, max_len=96, return_big_count=False,
+                          indices=None):
+    """Draw ``n`` camera-shake trajectories on ``device`` (``Trajectory(canvas, iters, max_len, expl).fit().x`` for each,
+    motion_blur/generate_trajectory.py:38-98) from the counter-based generator: trajectory k is a function of
+    (seed, first_index + k) only -- or of (seed, indices[k]) when explicit 63-bit ``indices`` are given.  ``expl`` is one
+    value or one per trajectory.  Returns a complex128 [n, iters] CUDA tensor that ``rasterize_psfs`` takes as is (no
+    host round trip)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("detectinblur_b200: trajectories are generated on a CUDA device here; "
+                           "motion_blur.generate_trajectory.Trajectory is the seeded host path")
+    ex = torch.as_tensor(np.array(np.broadcast_to(np.asarray(expl, dtype=np.float64), (n,))), device=device)
+    out = torch.empty((n, iters), dtype=torch.complex128, device=device)
+    big = torch.empty(n, dtype=torch.int32, device=device)
+    idx = None
+    if indices is not None:
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64).reshape(n), device=device)     # bit pattern of the uint64s
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib.dib_generate_trajectories(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_index),
+                                                      ctypes.c_void_p(idx.data_ptr()) if idx is not None else None, int(n), int(iters),
+                                                      float(max_len), float(canvas), ctypes.c_void_p(ex.data_ptr()),
+                                                      ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(big.data_ptr()),
+                                                      _stream_ptr(device)))
+    if return_big_count:
+        return out, big
     return out
 
 

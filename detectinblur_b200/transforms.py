@@ -58,7 +58,8 @@ def _in_worker():
 class BlurImage(object):
     def __init__(self, prob=0.5, blur_type=None, blur_exposure=None, use_stored_psfs=False, stored_psf_directory=None,
                  blur_image_in_transform=True, dont_center_psf=False, low_exposure=False, high_exposure=False,
-                 dilate_psf=False, LEHE_blur_seg=False, psf_backend="auto", device=None):
+                 dilate_psf=False, LEHE_blur_seg=False, psf_backend="auto", device=None, trajectory_backend="host",
+                 trajectory_seed=0):
         self.prob = prob
         self.blur_type = blur_type
         self.blur_exposure = blur_exposure
@@ -74,6 +75,13 @@ class BlurImage(object):
             raise ValueError("psf_backend must be 'auto', 'cuda' or 'defer'")
         self.psf_backend = psf_backend
         self.device = device
+        # "host": the reference's walk on numpy's global stream (bit-identical PSFs for a seeded pipeline).
+        # "cuda": opt-in -- the walk is drawn on the GPU from a counter-based generator (statistically equal, ~18 ms of
+        # host Python per PSF gone); the sample's key comes from python's `random`, numpy's stream is not consumed.
+        if trajectory_backend not in ("host", "cuda"):
+            raise ValueError("trajectory_backend must be 'host' or 'cuda'")
+        self.trajectory_backend = trajectory_backend
+        self.trajectory_seed = trajectory_seed
         if self.blur_image_in_transform:
             print("Blurring internally in transform on the GPU (detectinblur_b200; the reference's CPU Fourier path is replaced).")
         else:
@@ -131,16 +139,28 @@ class BlurImage(object):
             psf = psf_bank.load_stored_psf(self.stored_psf_directory, param_index, fraction_index, psf_index)
             blur_dict["stored_psf_source"] = (self.stored_psf_directory, param_index, fraction_index, psf_index)
         else:                                                                # :311-335
-            trajectory = Trajectory(canvas=256, max_len=96, expl=param).fit().fit()   # two walks drawn, the second kept
             center = not self.dont_center_psf
             side = 128 if center else 256
-            if self._backend() == "cuda":
-                dev = self.device if self.device is not None else torch.device("cuda")
-                psf = psf_ops.rasterize_psfs(trajectory.x[None], [fraction], dev, canvas=256, center=center, out_side=side,
-                                             dtype=torch.float64)[0].cpu().numpy()
+            if self.trajectory_backend == "cuda":
+                key = random.getrandbits(62)
+                if self._backend() == "cuda":
+                    dev = self.device if self.device is not None else torch.device("cuda")
+                    traj = psf_ops.generate_trajectories(1, param, self.trajectory_seed, dev, indices=[key])
+                    psf = psf_ops.rasterize_psfs(traj, [fraction], dev, canvas=256, center=center, out_side=side,
+                                                 dtype=torch.float64)[0].cpu().numpy()
+                else:
+                    psf = None
+                    deferred = {"trajectory": None, "trajectory_key": (self.trajectory_seed, key), "expl": param,
+                                "fraction": fraction, "center": center, "side": side}
             else:
-                psf = None
-                deferred = {"trajectory": trajectory.x, "fraction": fraction, "center": center, "side": side}
+                trajectory = Trajectory(canvas=256, max_len=96, expl=param).fit().fit()   # two walks drawn, the second kept
+                if self._backend() == "cuda":
+                    dev = self.device if self.device is not None else torch.device("cuda")
+                    psf = psf_ops.rasterize_psfs(trajectory.x[None], [fraction], dev, canvas=256, center=center, out_side=side,
+                                                 dtype=torch.float64)[0].cpu().numpy()
+                else:
+                    psf = None
+                    deferred = {"trajectory": trajectory.x, "fraction": fraction, "center": center, "side": side}
 
         if self.dilate_psf:                                                  # :338-342 (host scipy, as the reference)
             if psf is None:
@@ -196,10 +216,14 @@ def complete_blur_dicts(blur_dicts, device, dtype=torch.float16):
     by_shape = {}
     for k in todo:
         d = blur_dicts[k]["deferred_psf"]
-        by_shape.setdefault((d["center"], d["side"]), []).append(k)
-    for (center, side), members in by_shape.items():
-        traj = np.stack([blur_dicts[k]["deferred_psf"]["trajectory"] for k in members])
+        by_shape.setdefault((d["center"], d["side"], d["trajectory"] is None, d.get("trajectory_key", (0, 0))[0]), []).append(k)
+    for (center, side, on_device, seed), members in by_shape.items():
         frac = [blur_dicts[k]["deferred_psf"]["fraction"] for k in members]
+        if on_device:      # trajectory_backend="cuda": the walks are drawn here, one launch for the group
+            traj = psf_ops.generate_trajectories(len(members), [blur_dicts[k]["deferred_psf"]["expl"] for k in members], seed, device,
+                                                 indices=[blur_dicts[k]["deferred_psf"]["trajectory_key"][1] for k in members])
+        else:
+            traj = np.stack([blur_dicts[k]["deferred_psf"]["trajectory"] for k in members])
         dense = psf_ops.rasterize_psfs(traj, frac, device, canvas=256, center=center, out_side=side, dtype=torch.float64)
         host = dense.cpu().numpy()
         for j, k in enumerate(members):

@@ -167,6 +167,20 @@ DIB_API int dib_rasterize_psf(const double* traj, const double* fractions, int n
                       int out_side, void* out, int out_dtype, int32_t* offsets, double* scratch, void* stream);
 
 /*
+ * Camera-shake trajectories on the device: the random walk of motion_blur/generate_trajectory.py:38-98 (Trajectory.fit)
+ * with a counter-based generator instead of numpy's sequential global stream -- statistically, not bit-wise, equal to
+ * the reference (it removes ~18 ms of host Python per PSF from the on-the-fly path).  Trajectory k of the call is a pure
+ * function of (seed, index_k), index_k = indices[k] when `indices` (n device uint64) is given, else first_index + k.
+ *   expl        n per-trajectory `expl` parameters (0.005 / 0.001 / 0.00005 on the blur path)
+ *   out         n x iters complex128 samples (re = column, im = row), start point at canvas / 2, the layout
+ *               dib_rasterize_psf consumes
+ *   big_count   optional n int32: number of impulsive shakes (Trajectory.big_expl_count)
+ */
+DIB_API int dib_generate_trajectories(uint64_t seed, uint64_t first_index, const uint64_t* indices, int n, int iters,
+                              double max_len, double canvas, const double* expl, double* out, int32_t* big_count,
+                              void* stream);
+
+/*
  * One image of a fused normalize + bilinear resize + zero-padded batch pass (dib_resize_batch).
  */
 typedef struct dib_resize_image {

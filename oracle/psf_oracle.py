@@ -3,6 +3,7 @@
 Follows:
   * ``trajectory``     <- /root/reference/motion_blur/generate_trajectory.py:38-98 (Boracchi-Foi random walk,
                           numpy global MT19937 stream consumed in the same order)
+  * ``trajectory_philox`` the same walk driven by a counter-based generator: what the GPU generator computes
   * ``time_weights``   <- motion_blur/generate_PSF.py:47-56 (exposure-fraction time slicing, one fraction)
   * ``rasterize``      <- motion_blur/generate_PSF.py:31-77 (4-corner bilinear splat, sequential fp64 sums, /iters)
   * ``center``         <- motion_blur/generate_PSF.py:106-123 (weighted centroid, int() truncation, np.roll)
@@ -41,6 +42,56 @@ def trajectory(canvas=256, iters=2000, max_len=96, expl=0.005, rng=np.random):
         v = (v / float(np.abs(v))) * (max_len / float((iters - 1)))
         x[t + 1] = x[t] + v
     return x + complex(canvas / 2, canvas / 2)
+
+
+def philox4x32(seed, ctr_lo, ctr_hi):
+    """Philox4x32-10 (Salmon et al., SC'11; the generator family behind torch's CUDA randn): key = the 64-bit seed,
+    counter = (ctr_lo, ctr_hi) as two 64-bit halves.  Returns the four 32-bit output words."""
+    m32 = 0xFFFFFFFF
+    c = [ctr_lo & m32, (ctr_lo >> 32) & m32, ctr_hi & m32, (ctr_hi >> 32) & m32]
+    k0, k1 = seed & m32, (seed >> 32) & m32
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & m32, p1 & m32, ((p0 >> 32) ^ c[3] ^ k1) & m32, p0 & m32]
+        k0, k1 = (k0 + 0x9E3779B9) & m32, (k1 + 0xBB67AE85) & m32
+    return c
+
+
+def trajectory_philox(seed, index, expl, canvas=256, iters=2000, max_len=96):
+    """The counter-based variant of ``trajectory`` that dib_generate_trajectories evaluates (csrc/trajectory.cu): the
+    update equations of generate_trajectory.py:38-98 with the randomness of step t taken from
+    Philox(seed; counter t + 1, stream index): word 0 = shake test, word 1 = shake angle, words 2-3 = Box-Muller pair;
+    counter 0 = the four shape parameters.  Returns (x complex128[iters], number of impulsive shakes)."""
+    def u01(r):
+        return (float(r) + 0.5) * (1.0 / 4294967296.0)
+
+    r0 = philox4x32(seed, 0, index)
+    centripetal, prob_big_shake = 0.7 * u01(r0[0]), 0.2 * u01(r0[1])
+    gaussian_shake, ang = 10.0 * u01(r0[2]), 360.0 * u01(r0[3]) * (np.pi / 180.0)
+    step = max_len / float(iters - 1)
+    scale = expl if expl > 0 else step
+    vx, vy = np.cos(ang) * scale, np.sin(ang) * scale
+    x = y = 0.0
+    out = np.zeros(iters, dtype=np.complex128)
+    big = 0
+    for t in range(iters - 1):
+        r = philox4x32(seed, t + 1, index)
+        kx = ky = 0.0
+        if u01(r[0]) < prob_big_shake * expl:
+            a = np.pi + (u01(r[1]) - 0.5)
+            c, s = np.cos(a), np.sin(a)
+            kx, ky = 2.0 * (vx * c - vy * s), 2.0 * (vx * s + vy * c)
+            big += 1
+        rad = np.sqrt(-2.0 * np.log(u01(r[2])))
+        a = 6.28318530717958647692 * u01(r[3])
+        g0, g1 = rad * np.cos(a), rad * np.sin(a)
+        vx += kx + expl * (gaussian_shake * g0 - centripetal * x) * step
+        vy += ky + expl * (gaussian_shake * g1 - centripetal * y) * step
+        inv = step / np.sqrt(vx * vx + vy * vy)
+        vx, vy = vx * inv, vy * inv
+        x, y = x + vx, y + vy
+        out[t + 1] = complex(x, y)
+    return out + complex(canvas / 2, canvas / 2), big
 
 
 def time_weights(iters, fraction):

@@ -274,6 +274,67 @@ def test_fused_blur_normalize_with_resize(cuda):
     assert same.image_sizes == [(97, 131)]
 
 
+def test_gpu_trajectories_match_restatement_and_reference_statistics(cuda):
+    """dib_generate_trajectories: (1) equal to the CPU restatement of the same counter-based walk (<= 1e-8 px: libm vs
+    CUDA sin / cos / log differ in the last bits); (2) the walk's invariants; (3) its statistics against the reference's
+    MT19937 walk (host mirror, bit-identical to the reference): end-to-end displacement and bounding-box extent."""
+    import detectinblur_b200.psf_ops as ops
+    from detectinblur_b200.motion_blur.generate_trajectory import Trajectory
+    expl = [0.005, 0.001, 0.00005, 0.005]
+    x, big = ops.generate_trajectories(4, expl, 99, cuda, first_index=40, return_big_count=True)
+    assert x.dtype == torch.complex128 and tuple(x.shape) == (4, 2000)
+    xh = x.cpu().numpy()
+    for k in range(4):
+        want, wbig = po.trajectory_philox(99, 40 + k, expl[k])
+        assert np.abs(xh[k] - want).max() <= 1e-8, k
+        assert int(big[k]) == wbig
+        assert xh[k][0] == complex(128, 128)
+        assert abs(np.abs(np.diff(xh[k])).sum() - 96.0) < 1e-9           # every step has length max_len / (iters - 1)
+    # a pure function of (seed, index): any batch split, explicit indices
+    y = ops.generate_trajectories(2, expl[2:], 99, cuda, first_index=42)
+    z = ops.generate_trajectories(2, [expl[3], expl[0]], 99, cuda, indices=[43, 40])
+    assert torch.equal(y, x[2:]) and torch.equal(z[0], x[3]) and torch.equal(z[1], x[0])
+    assert not torch.equal(ops.generate_trajectories(1, 0.005, 100, cuda, first_index=40)[0], x[0])
+    # statistics against the reference walk
+    for e, tol in ((0.005, 0.25), (0.00005, 0.1)):
+        np.random.seed(4242)
+        host = np.stack([Trajectory(canvas=256, max_len=96, expl=e).fit().x for _ in range(64)])
+        gpu = ops.generate_trajectories(2048, e, 7, cuda).cpu().numpy()
+
+        def stats(t):
+            disp = np.abs(t[:, -1] - t[:, 0])
+            ext = np.maximum(t.real.max(1) - t.real.min(1), t.imag.max(1) - t.imag.min(1))
+            return disp, ext
+        for hs, gs in zip(stats(host), stats(gpu)):
+            se = np.sqrt(hs.var() / len(hs) + gs.var() / len(gs))
+            assert abs(hs.mean() - gs.mean()) <= 4 * se + tol, (e, hs.mean(), gs.mean(), se)
+    # device trajectories feed the rasteriser directly; a PSF's mass is its exposure fraction (generate_PSF.py:47-77)
+    psf = ops.rasterize_psfs(x, [1 / 10, 1 / 5, 1 / 2, 1], cuda, canvas=256, center=True, out_side=256, dtype=torch.float64)
+    sums = psf.sum(dim=(1, 2)).cpu().numpy()
+    for k, f in enumerate((1 / 10, 1 / 5, 1 / 2, 1)):
+        assert abs(sums[k] - po.time_weights(2000, f).sum() / 2000) < 1e-12
+
+
+def test_blur_image_gpu_trajectory_backend(cuda):
+    """BlurImage(trajectory_backend='cuda'): the walk is drawn on the GPU (numpy's stream untouched), directly or deferred."""
+    from detectinblur_b200.transforms import BlurImage, complete_blur_dicts
+    img = Image.fromarray(np.zeros((80, 90, 3), np.uint8))
+    random.seed(3)
+    np.random.seed(3)
+    state = np.random.get_state()[1].copy()
+    a = BlurImage(prob=1.0, blur_type=0.005, blur_exposure=1 / 5, blur_image_in_transform=False, psf_backend="cuda",
+                  trajectory_backend="cuda", trajectory_seed=5)(img, None, {})[2]
+    random.seed(3)
+    b = BlurImage(prob=1.0, blur_type=0.005, blur_exposure=1 / 5, blur_image_in_transform=False, psf_backend="defer",
+                  trajectory_backend="cuda", trajectory_seed=5)(img, None, {})[2]
+    assert np.array_equal(np.random.get_state()[1], state)              # no numpy draws in this mode
+    assert b["psf"] is None and b["deferred_psf"]["trajectory"] is None
+    psfs = complete_blur_dicts([b], cuda)
+    assert a["psf"].shape == (128, 128) and abs(a["psf"].sum() - 0.2) < 1e-3
+    assert np.array_equal(a["psf"], b["psf"]) and a["theta_rad"] == b["theta_rad"]
+    assert torch.equal(psfs[0].cpu(), torch.HalfTensor(b["psf"]))
+
+
 def test_packed_bank_upload_and_writer(cuda, tmp_path):
     """Packed sparse bank on the device: dib_unpack_psfs expands a batch's taps into the dense PSFs the reference uploads
     one by one (engine.py:84); the packed writer stores the same PSFs as the dense writer; complete_blur_dicts uses it."""

@@ -134,6 +134,20 @@ def test_transform_resize_port(golden_dir):
         assert np.abs(batch - g["batch_%d" % n]).max() <= 1e-6, n
 
 
+def test_philox_known_answers_and_counter_based_walk():
+    """Philox4x32-10 against the Random123 known-answer vectors; the counter-based walk keeps the reference walk's
+    invariants (unit-speed steps: total length == max_len; start at the canvas centre; a pure function of its key)."""
+    assert po.philox4x32(0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert po.philox4x32(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert po.philox4x32(0x299f31d0a4093822, 0x85a308d3243f6a88, 0x0370734413198a2e) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    x, big = po.trajectory_philox(1234, 7, 0.005, iters=400)
+    assert x[0] == complex(128, 128) and big >= 0
+    assert abs(np.abs(np.diff(x)).sum() - 96.0) < 1e-9
+    x2, _ = po.trajectory_philox(1234, 7, 0.005, iters=400)
+    x3, _ = po.trajectory_philox(1234, 8, 0.005, iters=400)
+    assert np.array_equal(x, x2) and not np.array_equal(x, x3)
+
+
 def test_normalize(golden_dir):
     g = _load(golden_dir, "normalize_case.npz")
     assert np.array_equal(bo.normalize_image(g["img"], g["mean"], g["std"]), g["out"])

@@ -120,6 +120,20 @@ def main():
     torch_us, _ = timed(torch_ops, args.repeats)
     tdiff = float((torch_ops() - il.tensors).abs().max())
     tbytes = sum(im.numel() * 4 for im in timgs) + il.tensors.numel() * 4
+    # trajectories on the device (opt-in, statistical parity): the whole on-the-fly chain without host RNG work
+    tr_expl = np.array([p for p, _ in cells] * 18)[:256]
+    g_us, _ = timed(lambda: ops.generate_trajectories(256, tr_expl, 1, dev), 5)
+
+    def chain():
+        t = ops.generate_trajectories(n, [p for p, _ in cells], 1, dev)
+        psf = ops.rasterize_psfs(t, frac, dev, canvas=256, center=True, out_side=128, dtype=torch.float32)
+        return bf.blur_batch(images, ops.compact_taps(psf, normalize=True), list(range(n)))
+
+    chain_us, _ = timed(chain, 10)
+    t0 = time.perf_counter()
+    for p, _ in cells:
+        Trajectory(canvas=256, max_len=96, expl=p).fit().fit()
+    host_traj_us = (time.perf_counter() - t0) / n * 1e6
     b1_dev = sum(c["device_us"] for c in per_cell)
     b1_wall = sum(c["wall_us"] for c in per_cell)
     print(json.dumps({
@@ -133,6 +147,10 @@ def main():
         "transform_8_images": {"batch_shape": list(il.tensors.shape), "fused_kernel_us": fused_us, "torch_ops_us": torch_us,
                                "algorithmic_bytes": tbytes, "fused_gbs": tbytes / (fused_us * 1e-6) / 1e9,
                                "max_abs_diff_vs_torch_cuda": tdiff},
+        "gpu_trajectories": {"batch256_device_us": g_us, "trajectories_per_s": 256 / (g_us * 1e-6),
+                             "chain15_generate_rasterize_compact_blur_us": chain_us,
+                             "chain15_images_per_s": n / (chain_us * 1e-6),
+                             "host_trajectory_us_each (Trajectory.fit().fit(), this box)": host_traj_us},
         "gpu_launches": bf.launch_count() - l0 + nt.launch_count(),
         "reference_cost_note": "the reference spends ~18 ms (trajectory) + ~45 ms (PSF splat loop) + O(taps) ATen launches per image",
     }))
