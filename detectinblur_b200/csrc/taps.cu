@@ -14,7 +14,7 @@
 
 namespace dib {
 
-constexpr int kCompactThreads = 256;
+constexpr int kCompactThreads = 1024;
 
 template <typename T>
 struct PsfNum;

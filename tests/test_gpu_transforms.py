@@ -244,6 +244,22 @@ def test_resize_normalize_batch_matches_reference_transform(cuda, golden_dir):
         assert np.abs(il16.tensors.float().cpu().numpy() - ref.tensors.numpy()).max() <= 1e-3
 
 
+def test_resize_pass_identity_scale_is_bit_exact_normalize(cuda):
+    """An image already at the target scale leaves the fused pass exactly as `normalize` leaves it (IEEE subtract and
+    divide, net_transforms.py:135-139): 3.2 M values against torch on the same device, several statistics."""
+    from detectinblur_b200 import net_transforms as nt
+    gen = torch.Generator().manual_seed(31)
+    img = (torch.rand((3, 800, 1333), generator=gen) * 1.2 - 0.1).to(cuda)
+    for mean, std in ((nt.CANONICAL_MEAN, nt.CANONICAL_STD), ([0.4695, 0.4461, 0.4068], [0.2005, 0.1962, 0.2006]),
+                      ([0.0, 0.5, 1.0], [1.0, 0.003, 700.0])):
+        tr = nt.GeneralizedRCNNTransform(800, 1333, mean, std, training=False)
+        il, _ = tr([img])
+        want = nt.normalize(img, mean, std)
+        assert il.image_sizes == [(800, 1333)] and tuple(il.tensors.shape) == (1, 3, 800, 1344)
+        assert torch.equal(il.tensors[0, :, :, :1333], want)
+        assert not il.tensors[0, :, :, 1333:].any()
+
+
 def test_fused_blur_normalize_with_resize(cuda):
     """blur at native size, then normalize + resize + batch: against oracle blur -> oracle transform."""
     from detectinblur_b200 import net_transforms as nt
