@@ -240,7 +240,10 @@ def run_own_arm(args, spec):
     host_batches = [torch.rand((B, C, H, W), generator=gen).pin_memory() for _ in range(n_rot)]
     batches = [hb.to(dev) for hb in host_batches]
     fused = bool(spec.get("fused_normalize"))
-    outs = torch.zeros((B, C, H, 1344 if fused else W), device=dev)
+    # results land in rows that start 16-byte aligned (pitch 1336 floats; 1344 for the padded batch of the fused workload),
+    # handed out as [:, :, :W] views -- what blur_batch allocates by default, and like the reference, whose result is a
+    # crop view of its padded accumulator (blur_functions.py:69)
+    outs = torch.zeros((B, C, H, 1344 if fused else (W + 3) // 4 * 4), device=dev)
     out_views = [outs[i, :, :, :W] for i in range(B)]
     norm_kw = dict(mean=[[0.485, 0.456, 0.406]] * B, std=[[0.229, 0.224, 0.225]] * B) if fused else {}
     traj, fracs = make_trajectories(spec, seed=1337 * rank)
@@ -399,6 +402,7 @@ def run_own_arm(args, spec):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec["desc"], "batch_per_gpu": B, "taps": taps,
+                       "output_layout": "rows 16-byte aligned (pitch %d floats), returned as [:, :, :W] views" % outs.shape[3],
                        "l2": "3 rotating input batches (3 x %.0f MB in, %.0f MB out) > 126 MB L2" % (
                            B * C * H * W * 4 / 1e6, B * C * H * W * 4 / 1e6),
                        "parallelism": "images sharded by rank, no collective on the hot path"},

@@ -7,7 +7,10 @@ plus ``blur_batch`` -- the batched call both are built on (one tap compaction la
 for the whole list instead of O(taps) launches and two host syncs per tap per image).
 
 Differences from the reference, all deliberate:
-  * results are new contiguous tensors (the reference returns a crop view of its padded accumulator);
+  * results are new tensors whose rows start 16-byte aligned: for a width that is not a multiple of 4 they are views
+    ``[:, :, :W]`` of a slightly wider allocation (the reference returns a view too -- a crop of its padded
+    accumulator, blur_functions.py:69); aligned rows let the tiled kernel store whole 16-byte quads without per-row
+    edge handling.  Pass ``outs=`` to ``blur_batch`` to write anywhere else;
   * CUDA tensors only: there is no CPU path;
   * fp32 images take the tiled kernel (FMA accumulation, <= 1e-5 from the reference loop; measured ~4e-7);
     ``exact=True`` (or ``DIB_EXACT=1``) forces the exact-order kernel, bit-identical to the reference's loop.
@@ -117,8 +120,11 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
             out = outs[k]
             if out.dtype != dtype or out.device != dev or out.dim() != 3 or out.stride(2) != 1:
                 raise ValueError("bad destination tensor for image %d" % k)
+        elif noise is not None and noise[k] is not None and tuple(noise[k].shape) == (C, H, W):
+            out = torch.empty_like(noise[k], dtype=dtype)            # a pre-drawn noise tensor shares the destination's layout
         else:
-            out = torch.empty((C, H, W), dtype=dtype, device=dev)
+            quad = 16 // img.element_size()
+            out = torch.empty((C, H, (W + quad - 1) // quad * quad), dtype=dtype, device=dev)[:, :, :W]    # 16-byte-aligned rows
         results.append(out)
         d = descs[k]
         d.src, d.dst = img.data_ptr(), out.data_ptr()

@@ -36,8 +36,9 @@ namespace dib {
 // columns) x kR * kCC FFMA2 of 16 bytes = 8 KB: it has to stay in the instruction cache (a 29 KB body stalled on
 // instruction fetch as often as it issued, profiles/round1_notes.md).  kR = 3 keeps a compute thread at ~130
 // registers, so 12 compute warps (three per SM sub-partition) fit beside the producer warpgroup; kR = 4 needs 172
-// registers, allows only 8 compute warps and measured 5 % slower; kR = 2 with 16 warps deadlocked on the box and
-// was not pursued.
+// registers, allows only 8 compute warps and measured 5 % slower; kR = 2 with 16 compute warps (104 registers) has
+// more warps to hide latency with but a third fewer FMAs per window load and measured 7 % slower.  (Its first build
+// hung: setmaxnreg.inc asked for more registers than the CTA's launch-time allocation holds -- see kLaunchRegs.)
 #ifndef DIB_R
 #define DIB_R 3
 #endif
@@ -60,9 +61,11 @@ constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: e
 constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
 constexpr int kProducerRegs = DIB_PRODUCER_REGS;   // setmaxnreg budgets; together they must fit the 64K-register file
-constexpr int kComputeRegs = ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8 > 232
-                                 ? 232
-                                 : ((65536 - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32)) / 8 * 8;
+// setmaxnreg moves registers inside the CTA's launch-time allocation (threads x the per-thread count the launch bound
+// allows, a multiple of 8); asking for more than the producers hand back blocks forever.
+constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8 > 255 ? 248 : (65536 / kThreads) / 8 * 8;
+constexpr int kComputeRegsRaw = (kThreads * kLaunchRegs - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32) / 8 * 8;
+constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
 static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
 constexpr int kTH = kWarpRows * kRows;      // 36 output rows per tile
 constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
@@ -93,6 +96,7 @@ struct TiledImage {
     int psf_index, nchunks;
     int epilogue;
     int zero_pad;         // DIB_PAD_ZERO128: pixels outside the image read as 0 instead of being mirrored
+    int aligned_out;      // every destination row starts 16-byte aligned (base, row pitch and channel pitch): lean row store
     int philox_slot;      // position in the caller's batch (Philox stream id)
     float noise_sd, gamma;
     float mean[4], std[4];
@@ -556,6 +560,55 @@ __device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int ske
     }
 }
 
+// Destination rows that all start 16-byte aligned (a pitched output, e.g. the padded batch or the wrapper's own
+// allocations) need no per-row skew, no head elements and -- except in the last column tile -- no tail: a third of the
+// general store's instructions.  Row q of the pass sits unskewed at obuf + q * kOutPitch.
+template <bool kAffine>
+__device__ __forceinline__ void store_rows_aligned(const TiledImage& im, int ch, int row0, int col0, float2 (&acc)[kR][kCC],
+                                                   uint32_t obuf, float scale, float shift) {
+    const int lane = threadIdx.x & 31;
+    const int wv = min(kWarpW, im.W - col0);
+    const int nrows = min(kRows, im.H - row0);
+    const int nq = wv >> 2, tail = wv & 3;                     // whole quads; leftover elements of the last column tile
+    const bool q0 = lane < nq, q1 = lane + 32 < nq, qt = lane < tail;
+    float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
+    const uint32_t sts0 = obuf + 4u * (uint32_t)(kCC * lane), lds0 = obuf + 16u * (uint32_t)lane;
+#pragma unroll
+    for (int r = 0; r < kRows; r += 2) {
+        if (r >= nrows) break;                                  // warp-uniform
+#pragma unroll
+        for (int c = 0; c < kCC; ++c) {
+            sts_f32(sts0 + 4u * c, r < kR ? acc[r % kR][c].x : acc[r % kR][c].y);
+            sts_f32(sts0 + 4u * (kOutPitch + c), r + 1 < kR ? acc[(r + 1) % kR][c].x : acc[(r + 1) % kR][c].y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (r + q < nrows) {
+                float* grow = g + (int64_t)q * im.dst_rp;
+                const uint32_t l = lds0 + 4u * (uint32_t)(q * kOutPitch);
+                if (q0) {
+                    float4 v = lds_v4(l);
+                    if (kAffine) { v.x = fmaf(v.x, scale, shift); v.y = fmaf(v.y, scale, shift); v.z = fmaf(v.z, scale, shift); v.w = fmaf(v.w, scale, shift); }
+                    *reinterpret_cast<float4*>(grow + 4 * lane) = v;
+                }
+                if (q1) {
+                    float4 v = lds_v4(l + 512u);
+                    if (kAffine) { v.x = fmaf(v.x, scale, shift); v.y = fmaf(v.y, scale, shift); v.z = fmaf(v.z, scale, shift); v.w = fmaf(v.w, scale, shift); }
+                    *reinterpret_cast<float4*>(grow + 4 * lane + 128) = v;
+                }
+                if (tail != 0 && qt) {
+                    float v = lds_f32(obuf + 4u * (uint32_t)(q * kOutPitch + 4 * nq + lane));
+                    if (kAffine) v = fmaf(v, scale, shift);
+                    grow[4 * nq + lane] = v;
+                }
+            }
+        }
+        __syncwarp();
+        g += 2 * im.dst_rp;
+    }
+}
+
 // Epilogue variants of the kernel: none; normalize only, applied as one FMA per pixel, x * (1/std) - mean/std (the
 // tiled kernel is not the bit-exact path, and an IEEE division per pixel would double its store cost); everything else.
 constexpr int kEpiNone = 0, kEpiAffine = 1, kEpiGeneral = 2;
@@ -573,6 +626,10 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
     ep.std = im.std[ch & 3];
     const bool norm = (im.epilogue & DIB_EPI_NORMALIZE) != 0;
     const float aff_scale = norm ? 1.0f / ep.std : 1.0f, aff_shift = norm ? -ep.mean / ep.std : 0.0f;
+    if (kEpi != kEpiGeneral && im.aligned_out) {
+        store_rows_aligned<kEpi == kEpiAffine>(im, ch, row0, col0, acc, obuf, aff_scale, aff_shift);
+        return;
+    }
     float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
     const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
     uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
@@ -754,6 +811,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.nchunks = m.prog_chunks;
         t.epilogue = im.epilogue;
         t.zero_pad = (im.pad_mode == DIB_PAD_ZERO128);
+        t.aligned_out = ((reinterpret_cast<uintptr_t>(im.dst) & 15u) == 0 && (im.dst_row_pitch & 3) == 0 && (im.dst_chan_pitch & 3) == 0) ? 1 : 0;
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
         any_epi |= (t.epilogue != 0);
         any_general |= (t.epilogue & ~DIB_EPI_NORMALIZE) != 0;

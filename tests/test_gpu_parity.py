@@ -141,6 +141,18 @@ def test_tiled_vs_oracle_seeded(dib, shape):
     assert np.array_equal(got_exact, want)
     got = bf.manual_blur(_cuda(img), _cuda(psfn), exact=False).cpu().numpy()
     assert np.abs(got.astype(np.float64) - want).max() <= TOL_FP32
+    # both row stores of the tiled kernel: the default result has 16-byte-aligned rows (a view of a wider allocation
+    # when W % 4 != 0), a caller-provided contiguous destination has not -- same values either way
+    ts = ops.compact_taps(_cuda(psfn), normalize=False)
+    dflt = bf.blur_batch([_cuda(img)], ts, [0])[0]
+    assert dflt.data_ptr() % 16 == 0 and dflt.stride(1) % 4 == 0 and tuple(dflt.shape) == shape
+    packed = torch.empty(shape, device="cuda")
+    res = bf.blur_batch([_cuda(img)], ts, [0], outs=[packed])[0]
+    assert res is packed and packed.is_contiguous()
+    odd = torch.empty((shape[0], shape[1], shape[2] + 1), device="cuda")[:, :, 1:]      # rows start 4 bytes off alignment
+    bf.blur_batch([_cuda(img)], ts, [0], outs=[odd])
+    assert torch.equal(dflt, packed) and torch.equal(dflt, odd)
+    assert np.array_equal(dflt.cpu().numpy().reshape(want.shape), got)
 
 
 @pytest.mark.parametrize("shape", [(3, 200, 300), (1, 65, 449), (2, 130, 1000), (3, 289, 331)])

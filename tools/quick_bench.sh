@@ -1,4 +1,4 @@
-for lib in detectinblur_b200/libdib.so; do
+for lib in detectinblur_b200/libdib*.so; do   # drop experimental builds next to libdib.so to compare them
   echo "== $lib"
   for w in cfg2 cfg3; do
     DIB_LIB_PATH=$PWD/$lib timeout 120 python bench.py --workload $w --steps 30 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
