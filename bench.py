@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5", "cfg2h"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -52,6 +52,11 @@ def workload_spec(name, batch):
         return dict(name="cfg2", batch=batch or 8, param_index=1, exposures=[0, 1, 2],
                     desc="gpu_blur of batch %dx3x800x1333 fp32, stored-format 128x128 PSFs, param_index 1 (expl 0.005), "
                          "low exposure (1/18, 1/10, 1/5)" % (batch or 8))
+    if name == "cfg2h":
+        return dict(name="cfg2h", batch=batch or 8, param_index=1, exposures=[0, 1, 2], half=True,
+                    desc="gpu_blur of batch %dx3x800x1333 fp16 (the dtype the reference's engines pass, engine.py:80): half rows "
+                         "widened while they are staged, fp32 accumulation, one rounding at the store; stored-format 128x128 "
+                         "PSFs, param_index 1, low exposure" % (batch or 8))
     if name == "cfg5":
         return dict(name="cfg5", batch=batch or 8, param_index=1, exposures=[0, 1, 2], fused_normalize=True,
                     desc="fused blur->normalize of batch %dx3x800x1333 fp32 into the zero-padded %dx3x800x1344 batch that feeds "
@@ -237,18 +242,22 @@ def run_own_arm(args, spec):
     # ---- synthetic inputs: images as torch.rand (seed 1337 + rank), PSFs rasterised on the GPU from seeded trajectories
     n_rot = 3     # rotating input batches: 3 x 102 MB of inputs (+ outputs) > 126 MB L2, nothing survives between steps
     gen = torch.Generator(device="cpu").manual_seed(1337 + rank)
-    host_batches = [torch.rand((B, C, H, W), generator=gen).pin_memory() for _ in range(n_rot)]
+    half = bool(spec.get("half"))
+    esize = 2 if half else 4
+    img_dtype = torch.float16 if half else torch.float32
+    host_batches = [torch.rand((B, C, H, W), generator=gen).to(img_dtype).pin_memory() for _ in range(n_rot)]
     batches = [hb.to(dev) for hb in host_batches]
     fused = bool(spec.get("fused_normalize"))
     # results land in rows that start 16-byte aligned (pitch 1336 floats; 1344 for the padded batch of the fused workload),
     # handed out as [:, :, :W] views -- what blur_batch allocates by default, and like the reference, whose result is a
     # crop view of its padded accumulator (blur_functions.py:69)
-    outs = torch.zeros((B, C, H, 1344 if fused else (W + 3) // 4 * 4), device=dev)
+    quad = 16 // esize
+    outs = torch.zeros((B, C, H, 1344 if fused else (W + quad - 1) // quad * quad), dtype=img_dtype, device=dev)
     out_views = [outs[i, :, :, :W] for i in range(B)]
     norm_kw = dict(mean=[[0.485, 0.456, 0.406]] * B, std=[[0.229, 0.224, 0.225]] * B) if fused else {}
     traj, fracs = make_trajectories(spec, seed=1337 * rank)
     psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
-    psfs = psfs16.float()                       # stored-format values (fp16 grid) in the image dtype
+    psfs = psfs16.to(img_dtype)                 # stored-format values (fp16 grid) in the image dtype
     host_psfs = psfs.cpu().pin_memory()
     tapset = ops.compact_taps(psfs, normalize=True)
     taps = tapset.counts
@@ -293,7 +302,7 @@ def run_own_arm(args, spec):
 
     # ---- kernel duration, live: the blur launch alone between events (same stream), averaged over the timed steps
     kern_ms = float(per_step.mean())
-    algo_bytes = ALGO_BYTES_PER_IMAGE * B
+    algo_bytes = ALGO_BYTES_PER_IMAGE * B * esize // 4
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -332,7 +341,7 @@ def run_own_arm(args, spec):
     if not args.no_e2e:
         # two streams ping-pong so that the H2D copy of step k + 1 overlaps the D2H copy of step k (PCIe is full duplex);
         # every step still moves its own inputs in and its own results out inside the timed region
-        host_outs = [torch.empty((B, C, H, W)).pin_memory() for _ in range(2)]
+        host_outs = [torch.empty((B, C, H, W), dtype=img_dtype).pin_memory() for _ in range(2)]
         streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
         e2e_steps = max(4, min(args.steps, 12))
 
@@ -364,7 +373,7 @@ def run_own_arm(args, spec):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "images/s",
-               "h2d_bytes_per_step": int(B * C * H * W * 4 + B * 128 * 128 * 4), "d2h_bytes_per_step": int(B * C * H * W * 4),
+               "h2d_bytes_per_step": int(B * C * H * W * esize + B * 128 * 128 * esize), "d2h_bytes_per_step": int(B * C * H * W * esize),
                "steps": e2e_steps, "api": "blur_image_list(images, blur_dicts, psfs) on pinned host buffers, two streams"}
 
     # ---- optional cross-shard verification: all-gather one checksum per rank (outside every timed region)
@@ -400,11 +409,12 @@ def run_own_arm(args, spec):
         line = {
             "metric": "blurred images/sec (800x1333 RGB)", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 i/o, f32 accumulate" if half else "f32",
+            "data": "synthetic",
             "config": {"workload": spec["desc"], "batch_per_gpu": B, "taps": taps,
                        "output_layout": "rows 16-byte aligned (pitch %d floats), returned as [:, :, :W] views" % outs.shape[3],
                        "l2": "3 rotating input batches (3 x %.0f MB in, %.0f MB out) > 126 MB L2" % (
-                           B * C * H * W * 4 / 1e6, B * C * H * W * 4 / 1e6),
+                           B * C * H * W * esize / 1e6, B * C * H * W * esize / 1e6),
                        "parallelism": "images sharded by rank, no collective on the hot path"},
             "clocks": clocks,
             "e2e": e2e,

@@ -16,7 +16,9 @@ Differences from the reference, all deliberate:
     ``exact=True`` (or ``DIB_EXACT=1``) forces the exact-order kernel, bit-identical to the reference's loop.
   * fp16 images (what the reference's engines pass) are widened, blurred with fp32 accumulation and rounded to half
     once: within 5e-3 of the reference's half loop, which rounds after every tap; ``exact=True`` reproduces that loop
-    bit for bit on the exact-order kernel.
+    bit for bit on the exact-order kernel.  The widening and the rounding happen inside the tiled kernel (half rows are
+    expanded while they are staged, results are packed at the store); batches it cannot take (noise / clamp / gamma
+    epilogues, unaligned caller-provided destinations, tiny images) go through two torch casts around the fp32 path.
 """
 import ctypes
 import math
@@ -97,7 +99,8 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     exact = _exact_default() if exact is None else exact
     if n == 0:
         return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
-    if images[0].dtype == torch.float16 and not exact:
+    if images[0].dtype == torch.float16 and not exact and not _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd,
+                                                                             clamp, philox_seed, gamma, pad_mode):
         return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode)
     dev = images[0].device
     dtype = images[0].dtype
@@ -166,12 +169,37 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     return BlurPlan(descs, n, tapset, dtype, algo, philox_seed, dev, results, keep)
 
 
+def _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, gamma, pad_mode):
+    """True when every image of a half batch can take the tiled kernel's fused half I/O (rows widened while they are
+    staged, fp32 accumulation, one rounding at the store): nothing but the normalize epilogue, destination rows 16-byte
+    aligned (the wrapper's own allocations are), sides above 64 px, PSFs with a tiled program."""
+    if noise is not None or noise_sd is not None or clamp is not None or philox_seed is not None or gamma is not None:
+        return False
+    if pad_mode is not None and pad_mode not in (_lib.PAD_REFLECT128, _lib.PAD_ZERO128):
+        return False
+    for k, img in enumerate(images):
+        if img.dim() != 3 or img.dtype != torch.float16:
+            return False
+        if psf_indices[k] < 0:
+            return False                                   # pass-through images go through the generic kernel's epilogue
+        if img.shape[1] <= 64 or img.shape[2] <= 64 or tapset is None or tapset.side > 129:
+            return False
+        m = tapset.meta[int(psf_indices[k])]
+        if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM):
+            return False
+        if outs is not None and outs[k] is not None:
+            o = outs[k]
+            if o.dtype != torch.float16 or o.dim() != 3 or o.data_ptr() % 16 or o.stride(1) % 8 or (o.shape[0] > 1 and o.stride(0) % 8):
+                return False
+    return True
+
+
 class _HalfPlan(object):
     """fp16 images on the fast path: widen to fp32, blur with fp32 accumulation (tiled kernel where eligible), round to
     half ONCE.  More accurate than the reference's half loop, which rounds after every tap (it differs from it by up to
     ~5e-3 on [0,1] images, SURVEY.md section 7 "dtype contract"); ``exact=True`` reproduces the half loop bit for bit.
-    The two casts are plain torch element-wise copies around the kernel; fusing them into the kernel's staging and store
-    is listed as next work in DESIGN.md."""
+    Fallback of the fused half I/O of the tiled kernel (``_half_tiled_ok``): the two casts are plain torch element-wise
+    copies around the fp32 path."""
 
     def __init__(self, images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode=None):
         self.images, self.tapset, self.psf_indices, self.outs = images, tapset, psf_indices, outs

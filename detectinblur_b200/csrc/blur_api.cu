@@ -9,15 +9,22 @@ namespace dib {
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
                    int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, cudaStream_t st);
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, cudaStream_t st);
 
 static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
-    if (meta_host == nullptr || io_dtype != DIB_F32 || im.psf_index < 0) return false;
+    if (meta_host == nullptr || im.psf_index < 0) return false;
+    if (io_dtype == DIB_F16) {
+        // half I/O: fp32 accumulation, rounded to half once (the reference's half loop rounds after every tap -- callers
+        // that need its bits pass DIB_ALGO_GENERIC).  Needs 16-byte-aligned destination rows and at most the normalize epilogue.
+        if ((reinterpret_cast<uintptr_t>(im.dst) & 15u) || (im.dst_row_pitch & 7) || (im.dst_chan_pitch & 7)) return false;
+        if (reinterpret_cast<uintptr_t>(im.src) & 1u) return false;
+        if (im.epilogue & ~DIB_EPI_NORMALIZE) return false;
+    }
     // reflect-101 or zero padding about centre 63; tiny images (the reference's own zero-padding case) stay on the generic kernel
     if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return false;
     const dib_psf_meta& m = meta_host[im.psf_index];
     if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return false;
-    if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) return false;
+    if (io_dtype == DIB_F32 && ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u)) return false;
     return true;
 }
 }  // namespace dib
@@ -71,8 +78,8 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
                 order[n_sel++] = k;
                 tiled_mask |= 1u << k;
             } else if (algo == DIB_ALGO_TILED) {
-                set_error("dib_blur_batch: image %d is not eligible for the tiled kernel (fp32, reflect mode, sides > 64, "
-                          "PSF with a tiled program and host meta required)", k);
+                set_error("dib_blur_batch: image %d is not eligible for the tiled kernel (reflect or zero mode, sides > 64, PSF with a "
+                          "tiled program and host meta; half images: 16-byte-aligned destination rows, normalize epilogue at most)", k);
                 return DIB_ERR_UNSUPPORTED;
             }
         }
@@ -90,7 +97,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     }
     int nl = 0;
     if (n_sel > 0) {
-        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, st);
+        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, io_dtype, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

@@ -49,7 +49,7 @@ namespace dib {
 #define DIB_WARP_COLS 2
 #endif
 #ifndef DIB_PRODUCER_REGS
-#define DIB_PRODUCER_REGS 40
+#define DIB_PRODUCER_REGS 56      // 12 x 32 x 152 + 4 x 32 x 56 = 65536: the compute warps cannot use the difference to 40 anyway
 #endif
 constexpr int kR = DIB_R;                   // row pairs per thread
 constexpr int kRows = 2 * kR;               // output rows per thread (= rotation period of the register window)
@@ -71,7 +71,9 @@ constexpr int kTH = kWarpRows * kRows;      // 36 output rows per tile
 constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
 constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
 constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
-constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 3) + 3) / 4 * 4;   // 472 floats (16 B multiple)
+// Staged row: tile + halo + the row's skew (<= 3 floats for fp32 rows, <= 7 for half rows), rounded to 8 floats so that the
+// second half of a row's bytes -- where half-precision rows land before they are widened in place -- is 16-byte aligned.
+constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 7) + 7) / 8 * 8;   // 480 floats
 constexpr int kOutPitch = kWarpW + 4;       // one staged output row of a warp (skew <= 3)
 constexpr int kHdrBytes = 64;
 constexpr int kAuxBytes = (kChunkDataMax + 15) / 16 * 16;          // segment records + weights of one chunk
@@ -81,13 +83,13 @@ constexpr int kStageBytes = kHdrBytes + kAuxBytes + kRowTabBytes + kTileBytes;
 constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;    // two staged rows per compute warp
 constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 64;    // + 4 mbarriers + 2 tile-ticket slots
 static_assert(kRowsMax <= kProducerWarps * 32, "one staged row per producer thread");
-static_assert(kPitch % 4 == 0 && kPitch >= kTW + kChunkGroups * kGroupW - 1 + 3, "pitch must hold tile + halo + skew");
+static_assert(kPitch % 8 == 0 && kPitch >= kTW + kChunkGroups * kGroupW - 1 + 7, "pitch must hold tile + halo + skew");
 static_assert(kStageBytes % 16 == 0, "stage must keep 16-byte alignment");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 struct TiledImage {
-    const float* src;
-    float* dst;
+    const void* src;      // float or __half (kernel template), pitches in elements
+    void* dst;
     const float* noise;
     int64_t src_rp, src_cp, dst_rp, dst_cp;
     int C, H, W;
@@ -288,7 +290,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     const int cl = st.j0 - st.rec.dx_hi;                                  // image column of staged column 0
     const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;            // last staged image column
     const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;              // in-image part [xa, xb1)
-    const float* plane = im.src + (int64_t)st.ch * im.src_cp;
+    const float* plane = static_cast<const float*>(im.src) + (int64_t)st.ch * im.src_cp;
     fence_proxy_async();   // order the consumers' generic-proxy reads of this buffer before the async-proxy writes
     if (pt == 0) {
         StageHdr h;
@@ -352,6 +354,145 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
     mbar_arrive_expect_tx(bar, bytes);
     cp_async_mbar_arrive(bar);
+}
+
+// Half-precision I/O: the same stage built from __half rows.  Thread t places row t's 16-byte-aligned interior, as
+// halves, in the SECOND half of the row's bytes with one TMA bulk copy (skewed so that global and shared addresses
+// agree mod 16 bytes); when the stage's copies have landed (`landed` barrier) the producer warps widen the rows in place,
+// front to back -- the float written for element p ends at byte 4p + 4, never past a half still to be read at byte
+// 2 * kPitch + 2p' of a later group -- and then fill in what TMA cannot move: the <= 7 + 7 unaligned end elements and the mirrored (or zero) border columns,
+// read straight from global memory.  The consumers see exactly the fp32 tile of the float path.
+__device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* landed,
+                                                 uint32_t landed_parity, uint64_t* full, int pt) {
+    const TiledImage& im = p.img[st.img];
+    const int lane = pt & 31, pw = pt >> 5;
+    const int sr = lane * kProducerWarps + pw;
+    const int rt = st.i0 - st.rec.dy_hi;
+    const int nrows = kTH + st.rec.dy_hi - st.rec.dy_lo;
+    const int cl = st.j0 - st.rec.dx_hi;
+    const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;
+    const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;
+    const __half* plane = static_cast<const __half*>(im.src) + (int64_t)st.ch * im.src_cp;
+    fence_proxy_async();
+    if (pt == 0) {
+        StageHdr h;
+        h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
+        h.first_chunk = (st.chunk == 0);
+        h.last_chunk = (st.chunk + 1 == im.nchunks);
+        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
+        *sm.hdr = h;
+    }
+    uint32_t bytes = 0;
+    const __half* gp = plane;
+    int ro = sr * kPitch;
+    int xa_al = cl, xb_al = cl;
+    const bool in_rows = sr < nrows;
+    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
+    if (in_rows && !zero_row) {
+        gp = plane + (int64_t)reflect101(rt + sr, im.H) * im.src_rp;
+        if (xb1 > xa) {
+            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 1);       // in halves
+            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 7u);
+            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 7u);
+            if (xb_al <= xa_al) xa_al = xb_al = xa;
+        }
+        ro += (int)((uint32_t)(cl - xa_al) & 7u);       // skew: (xa_al - cl + skew) is a multiple of 8
+        const uint32_t nb = (uint32_t)(xb_al - xa_al) * 2u;
+        if (nb) {
+            __half* hrow = reinterpret_cast<__half*>(sm.tile + sr * kPitch) + kPitch;      // the row's second half
+            tma_bulk_g2s(hrow + (ro - sr * kPitch) + (xa_al - cl), gp + xa_al, nb, landed);
+            bytes += nb;
+        }
+    }
+    if (sr < kRowsMax) sm.rowtab[sr] = ro;
+    if (pt == 32) {
+        const uint32_t nb = (uint32_t)(kChunkSegBytes + kStepBytes * (st.rec.wsteps + 1));
+        tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, landed);
+        bytes += nb;
+    }
+    mbar_arrive_expect_tx(landed, bytes);
+    // the <= 7 + 7 unaligned end elements of the row: independent global loads, in flight while the bulk copies land
+    __half head[7], tail[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        head[j] = (in_rows && !zero_row && xa + j < xa_al) ? gp[xa + j] : __half(0.0f);
+        tail[j] = (in_rows && !zero_row && xb_al + j < xb1) ? gp[xb_al + j] : __half(0.0f);
+    }
+    mbar_wait(landed, landed_parity);
+    float* drow = sm.tile + ro - cl;                  // drow[col] addresses image column col
+    // Widen the aligned interiors in place.  A warp takes the rows its own lanes placed, one row at a time, a lane per
+    // group of 8 elements: every lane first reads its 16 bytes of halves, then -- after a warp barrier -- writes its 32
+    // bytes of floats.  Within a round of 32 groups the floats land on halves that the round has already read (a float
+    // group ends at byte 32 g + 32, the half group it may reach starts at 2 * kPitch + 16 g); rounds ascend along the row.
+    {
+        const int my_n8 = (in_rows && !zero_row) ? (xb_al - xa_al) >> 3 : 0;
+        const int my_off = ro - cl + xa_al;                                 // float index of the row's first aligned element
+        for (int l = 0; l < 32; ++l) {
+            if (l * kProducerWarps + pw >= nrows) break;
+            const int n8 = __shfl_sync(0xffffffffu, my_n8, l);
+            const int off = __shfl_sync(0xffffffffu, my_off, l);
+            const int r2 = l * kProducerWarps + pw;
+            const float* frow = sm.tile + off;
+            const uint4* hsrc = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(sm.tile + r2 * kPitch) + kPitch +
+                                                               (off - r2 * kPitch));
+            // a row holds at most kPitch / 8 = 60 groups: two rounds, both read before either is written
+            static_assert(kPitch / 8 <= 64, "two rounds of 32 groups cover a staged row");
+            const bool g0 = lane < n8, g1 = lane + 32 < n8;
+            uint4 ha = make_uint4(0u, 0u, 0u, 0u), hb = ha;
+            if (g0) ha = hsrc[lane];
+            if (g1) hb = hsrc[lane + 32];
+            __syncwarp();
+            float4* fdst = reinterpret_cast<float4*>(const_cast<float*>(frow)) + 2 * lane;
+            if (g0) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ha.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ha.y));
+                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&ha.z));
+                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&ha.w));
+                fdst[0] = make_float4(a.x, a.y, b.x, b.y);
+                fdst[1] = make_float4(c.x, c.y, d.x, d.y);
+            }
+            if (g1) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hb.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hb.y));
+                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&hb.z));
+                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&hb.w));
+                fdst[64] = make_float4(a.x, a.y, b.x, b.y);
+                fdst[65] = make_float4(c.x, c.y, d.x, d.y);
+            }
+        }
+        __syncwarp();
+    }
+    if (in_rows && zero_row) {
+        for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
+    } else if (in_rows) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (xa + j < xa_al) drow[xa + j] = __half2float(head[j]);
+            if (xb_al + j < xb1) drow[xb_al + j] = __half2float(tail[j]);
+        }
+    }
+    if (cl < 0 || cr >= im.W) {
+        // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels, or zeros in zero-padding mode.  All
+        // producer threads share the (row, column) pairs; the row table written above tells where each row sits.
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
+        const int total = nrows * ncols;
+#pragma unroll 4
+        for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
+            const int r2 = idx / ncols, k = idx - r2 * ncols;
+            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
+            const int irow = rt + r2;
+            float v = 0.0f;
+            bool write = true;
+            if (im.zero_pad) {
+                write = irow >= 0 && irow < im.H;            // rows outside the image are already all zeros
+            } else {
+                v = __half2float(plane[(int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W)]);
+            }
+            if (write) sm.tile[sm.rowtab[r2] - cl + col] = v;
+        }
+    }
+    mbar_arrive(full);          // release: this thread's shared-memory writes are visible to whoever observes the phase
 }
 
 // ---------------------------------------------------------------- compute
@@ -571,7 +712,7 @@ __device__ __forceinline__ void store_rows_aligned(const TiledImage& im, int ch,
     const int nrows = min(kRows, im.H - row0);
     const int nq = wv >> 2, tail = wv & 3;                     // whole quads; leftover elements of the last column tile
     const bool q0 = lane < nq, q1 = lane + 32 < nq, qt = lane < tail;
-    float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
+    float* g = static_cast<float*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
     const uint32_t sts0 = obuf + 4u * (uint32_t)(kCC * lane), lds0 = obuf + 16u * (uint32_t)lane;
 #pragma unroll
     for (int r = 0; r < kRows; r += 2) {
@@ -609,11 +750,61 @@ __device__ __forceinline__ void store_rows_aligned(const TiledImage& im, int ch,
     }
 }
 
+// Half-precision destination with 16-byte-aligned rows: eight values per lane and row, rounded to half once.
+template <bool kAffine>
+__device__ __forceinline__ void store_rows_aligned_half(const TiledImage& im, int ch, int row0, int col0, float2 (&acc)[kR][kCC],
+                                                        uint32_t obuf, float scale, float shift) {
+    const int lane = threadIdx.x & 31;
+    const int wv = min(kWarpW, im.W - col0);
+    const int nrows = min(kRows, im.H - row0);
+    const int n8 = wv >> 3, tail = wv & 7;
+    const bool q0 = lane < n8, qt = lane < tail;
+    __half* g = static_cast<__half*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
+    const uint32_t sts0 = obuf + 4u * (uint32_t)(kCC * lane), lds0 = obuf + 32u * (uint32_t)lane;
+#pragma unroll
+    for (int r = 0; r < kRows; r += 2) {
+        if (r >= nrows) break;
+#pragma unroll
+        for (int c = 0; c < kCC; ++c) {
+            sts_f32(sts0 + 4u * c, r < kR ? acc[r % kR][c].x : acc[r % kR][c].y);
+            sts_f32(sts0 + 4u * (kOutPitch + c), r + 1 < kR ? acc[(r + 1) % kR][c].x : acc[(r + 1) % kR][c].y);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (r + q < nrows) {
+                __half* grow = g + (int64_t)q * im.dst_rp;
+                const uint32_t l = lds0 + 4u * (uint32_t)(q * kOutPitch);
+                if (q0) {
+                    float4 a = lds_v4(l), b = lds_v4(l + 16u);
+                    if (kAffine) {
+                        a.x = fmaf(a.x, scale, shift); a.y = fmaf(a.y, scale, shift); a.z = fmaf(a.z, scale, shift); a.w = fmaf(a.w, scale, shift);
+                        b.x = fmaf(b.x, scale, shift); b.y = fmaf(b.y, scale, shift); b.z = fmaf(b.z, scale, shift); b.w = fmaf(b.w, scale, shift);
+                    }
+                    uint4 o;
+                    *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(a.x, a.y);
+                    *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(a.z, a.w);
+                    *reinterpret_cast<__half2*>(&o.z) = __floats2half2_rn(b.x, b.y);
+                    *reinterpret_cast<__half2*>(&o.w) = __floats2half2_rn(b.z, b.w);
+                    *reinterpret_cast<uint4*>(grow + 8 * lane) = o;
+                }
+                if (tail != 0 && qt) {
+                    float v = lds_f32(obuf + 4u * (uint32_t)(q * kOutPitch + 8 * n8 + lane));
+                    if (kAffine) v = fmaf(v, scale, shift);
+                    grow[8 * n8 + lane] = __float2half_rn(v);
+                }
+            }
+        }
+        __syncwarp();
+        g += 2 * im.dst_rp;
+    }
+}
+
 // Epilogue variants of the kernel: none; normalize only, applied as one FMA per pixel, x * (1/std) - mean/std (the
 // tiled kernel is not the bit-exact path, and an IEEE division per pixel would double its store cost); everything else.
 constexpr int kEpiNone = 0, kEpiAffine = 1, kEpiGeneral = 2;
 
-template <int kEpi>
+template <int kEpi, bool kHalf>
 __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0,
                                            float2 (&acc)[kR][kCC], uint32_t obuf) {
     const int lane = threadIdx.x & 31;
@@ -626,11 +817,16 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
     ep.std = im.std[ch & 3];
     const bool norm = (im.epilogue & DIB_EPI_NORMALIZE) != 0;
     const float aff_scale = norm ? 1.0f / ep.std : 1.0f, aff_shift = norm ? -ep.mean / ep.std : 0.0f;
+    if constexpr (kHalf) {
+        // the launcher only admits half images whose destination rows are 16-byte aligned and whose epilogue is affine
+        store_rows_aligned_half<kEpi == kEpiAffine>(im, ch, row0, col0, acc, obuf, aff_scale, aff_shift);
+        return;
+    }
     if (kEpi != kEpiGeneral && im.aligned_out) {
         store_rows_aligned<kEpi == kEpiAffine>(im, ch, row0, col0, acc, obuf, aff_scale, aff_shift);
         return;
     }
-    float* g = im.dst + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
+    float* g = static_cast<float*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
     const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
     uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
     const uint32_t rp_lo = (uint32_t)im.dst_rp;
@@ -676,19 +872,23 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
 
 // ---------------------------------------------------------------- kernel
 // kEpi selects the epilogue variant (kEpiNone / kEpiAffine / kEpiGeneral); batches without one run the leanest.
-template <int kEpi>
+template <int kEpi, bool kHalf>
 __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
     uint64_t* full = bars;          // [2] producers -> consumers: stage loaded
     uint64_t* empty = bars + 2;     // [2] consumers -> producers: stage may be refilled
-    int* tile_slots = reinterpret_cast<int*>(bars + 4);
+    uint64_t* landed = bars + 4;    // [2] half I/O only: the stage's bulk copies have arrived, rows may be widened
+    int* tile_slots = reinterpret_cast<int*>(bars + 6);
     const int warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 2 * kProducerWarps * 32);   // per producer thread: one arrive.expect_tx + one cp.async arrive
-        mbar_init(&full[1], 2 * kProducerWarps * 32);
+        // float: per producer thread one arrive.expect_tx + one cp.async arrive; half: one plain arrive after widening
+        mbar_init(&full[0], (kHalf ? 1 : 2) * kProducerWarps * 32);
+        mbar_init(&full[1], (kHalf ? 1 : 2) * kProducerWarps * 32);
+        mbar_init(&landed[0], kProducerWarps * 32);
+        mbar_init(&landed[1], kProducerWarps * 32);
         mbar_init(&empty[0], kComputeWarps);
         mbar_init(&empty[1], kComputeWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -716,8 +916,12 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             const StageSmem sm = stage_smem(smem, b);
             if (cur.tile < 0) {
                 if (pt == 0) sm.hdr->tile = -1;
-                mbar_arrive_expect_tx(&full[b], 0);
-                cp_async_mbar_arrive(&full[b]);
+                if constexpr (kHalf) {
+                    mbar_arrive(&full[b]);
+                } else {
+                    mbar_arrive_expect_tx(&full[b], 0);
+                    cp_async_mbar_arrive(&full[b]);
+                }
                 // this CTA has stopped fetching; the last CTA to get here rewinds the scheduler for the next launch
                 if (pt == 0) {
                     __threadfence();
@@ -729,7 +933,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
                 }
                 break;
             }
-            issue_stage(p, cur, sm, &full[b], pt);
+            if constexpr (kHalf)
+                issue_stage_half(p, cur, sm, &landed[b], (uint32_t)((n >> 1) & 1), &full[b], pt);
+            else
+                issue_stage(p, cur, sm, &full[b], pt);
             cur = nxt;
         }
     } else {
@@ -763,7 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
-            if (h.last_chunk && active) store_rows<kEpi>(p, im, h.ch, row0, col0, acc, obuf);
+            if (h.last_chunk && active) store_rows<kEpi, kHalf>(p, im, h.ch, row0, col0, acc, obuf);
         }
     }
 }
@@ -776,16 +983,18 @@ int tiled_tile_counts(int H, int W, int* tiles_y, int* tiles_x) {
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, cudaStream_t st) {
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, cudaStream_t st) {
     static thread_local int sm_count = 0;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
     DIB_CUDA(cudaGetDevice(&dev));
     if (attr_set_dev != dev) {
         DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set_dev = dev;
     }
     TiledParams p;
@@ -795,8 +1004,8 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         const dib_image& im = images[order[k]];
         const dib_psf_meta& m = meta_host[im.psf_index];
         TiledImage& t = p.img[k];
-        t.src = static_cast<const float*>(im.src);
-        t.dst = static_cast<float*>(im.dst);
+        t.src = im.src;
+        t.dst = im.dst;
         t.noise = static_cast<const float*>(im.noise);
         t.src_rp = im.src_row_pitch;
         t.src_cp = im.src_chan_pitch;
@@ -831,12 +1040,22 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_offset = offset;
     p.sched = sched;
     const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
-    if (any_general)
-        blur_tiled_kernel<kEpiGeneral><<<grid, kThreads, kSmemBytes, st>>>(p);
-    else if (any_epi)
-        blur_tiled_kernel<kEpiAffine><<<grid, kThreads, kSmemBytes, st>>>(p);
-    else
-        blur_tiled_kernel<kEpiNone><<<grid, kThreads, kSmemBytes, st>>>(p);
+    if (io_dtype == DIB_F16) {
+        if (any_general) {
+            set_error("dib_blur_batch: half images with a noise / clamp / gamma epilogue do not take the tiled kernel");
+            return DIB_ERR_UNSUPPORTED;
+        }
+        if (any_epi)
+            blur_tiled_kernel<kEpiAffine, true><<<grid, kThreads, kSmemBytes, st>>>(p);
+        else
+            blur_tiled_kernel<kEpiNone, true><<<grid, kThreads, kSmemBytes, st>>>(p);
+    } else if (any_general) {
+        blur_tiled_kernel<kEpiGeneral, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+    } else if (any_epi) {
+        blur_tiled_kernel<kEpiAffine, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+    } else {
+        blur_tiled_kernel<kEpiNone, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+    }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;
 }

@@ -367,3 +367,43 @@ def test_half_images_fast_path_tolerance(dib, golden_dir):
         want = bo.manual_blur(g["img_%d" % n].astype(np.float16).astype(np.float32), g["psfn_f16_%d" % n].astype(np.float32))
         assert np.abs(got.cpu().numpy().astype(np.float64) - want.astype(np.float16).astype(np.float64)).max() <= 1e-3, n
     assert worst > 0          # the two really are different computations
+
+
+@pytest.mark.parametrize("shape", [(3, 200, 300), (1, 65, 449), (2, 130, 1001), (3, 289, 331), (3, 480, 640)])
+def test_half_io_inside_the_tiled_kernel(dib, shape):
+    """Half images take the tiled kernel directly: rows are widened while they are staged (odd widths give rows at every
+    2-byte phase), accumulation is fp32, results are rounded to half once at the store.  Bit-identical to widening with
+    torch, running the fp32 tiled kernel and rounding with torch (the fallback path), in reflect and zero-padding mode."""
+    bf, ops = dib
+    from detectinblur_b200 import _lib
+    rng = np.random.default_rng(sum(shape) + 7)
+    img = _cuda(rng.random(shape, dtype=np.float32), torch.float16)
+    np.random.seed(shape[2])
+    psf16, _ = po.stored_psf(0.001, 1 / 2, np.random)
+    ts = ops.compact_taps(_cuda(po.crop128(psf16)), normalize=True)          # half PSF, as the engines upload it
+    for pad in (None, _lib.PAD_ZERO128):
+        before = bf.launch_count()
+        fused = bf.blur_batch([img], ts, [0], pad_mode=pad)[0]
+        assert bf.launch_count() == before + 1                                # one kernel, no cast passes
+        assert fused.dtype == torch.float16 and tuple(fused.shape) == shape and fused.data_ptr() % 16 == 0
+        fallback = bf.blur_batch([img], ts, [0], pad_mode=pad, clamp=[False])[0]    # any epilogue request takes the cast path
+        assert torch.equal(fused, fallback)
+        want = bo.manual_blur(img.float().cpu().numpy(), ts_weights(ts), pad_mode=bo.PAD_ZERO if pad is not None else None)
+        err = np.abs(fused.float().cpu().numpy().reshape(want.shape) - want).max()
+        assert err <= 1e-3                                                     # one half rounding of values in [0, 1]
+    # fused normalize into a half destination, and a caller-provided unaligned destination (falls back, same values)
+    mean, std = [[0.485, 0.456, 0.406][:shape[0]]], [[0.229, 0.224, 0.225][:shape[0]]]
+    a = bf.blur_batch([img], ts, [0], mean=mean, std=std)[0]
+    b = bf.blur_batch([img.float()], ts, [0], mean=mean, std=std)[0]
+    assert a.dtype == torch.float16 and (a.float() - b).abs().max().item() <= 4e-3
+    odd = torch.empty((shape[0], shape[1], shape[2] + 1), dtype=torch.float16, device="cuda")[:, :, 1:]
+    bf.blur_batch([img], ts, [0], outs=[odd])
+    assert torch.equal(odd, bf.blur_batch([img], ts, [0])[0])
+
+
+def ts_weights(ts):
+    """Dense normalised PSF rebuilt from a tap set (what the oracle's manual_blur takes)."""
+    ys, xs, ws = ts.taps(0)
+    dense = np.zeros((ts.side, ts.side), dtype=np.float32)
+    dense[ys, xs] = ws
+    return dense
