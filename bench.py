@@ -341,7 +341,7 @@ def run_own_arm(args, spec):
     if not args.no_e2e:
         # two streams ping-pong so that the H2D copy of step k + 1 overlaps the D2H copy of step k (PCIe is full duplex);
         # every step still moves its own inputs in and its own results out inside the timed region
-        host_outs = [torch.empty((B, C, H, W), dtype=img_dtype).pin_memory() for _ in range(2)]
+        host_outs = [torch.empty((B, C, H, (W + quad - 1) // quad * quad), dtype=img_dtype).pin_memory() for _ in range(2)]
         streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
         e2e_steps = max(4, min(args.steps, 12))
 
@@ -355,7 +355,11 @@ def run_own_arm(args, spec):
                 images = [dbatch[i] for i in range(B)]
                 bf.blur_image_list(images, [{"blurring": True}] * B, [dpsf[i] for i in range(B)])
                 for i in range(B):
-                    host_outs[k % 2][i].copy_(images[i], non_blocking=True)
+                    # results are [:, :, :W] views of row-aligned buffers: copy the whole buffer (one plain async memcpy per
+                    # image) instead of letting torch gather the view with an extra device kernel first
+                    r = images[i]
+                    full = r.as_strided((C, H, r.stride(1)), (r.stride(0), r.stride(1), 1))
+                    host_outs[k % 2][i, :, :, :r.stride(1)].copy_(full, non_blocking=True)
 
         for k in range(4):
             e2e_step(k)
@@ -373,7 +377,7 @@ def run_own_arm(args, spec):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "images/s",
-               "h2d_bytes_per_step": int(B * C * H * W * esize + B * 128 * 128 * esize), "d2h_bytes_per_step": int(B * C * H * W * esize),
+               "h2d_bytes_per_step": int(B * C * H * W * esize + B * 128 * 128 * esize), "d2h_bytes_per_step": int(B * C * H * ((W + quad - 1) // quad * quad) * esize),
                "steps": e2e_steps, "api": "blur_image_list(images, blur_dicts, psfs) on pinned host buffers, two streams"}
 
     # ---- optional cross-shard verification: all-gather one checksum per rank (outside every timed region)
