@@ -334,21 +334,20 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         bytes += nb;
     }
     if (cl < 0 || cr >= im.W) {
-        // mirrored columns [cl, xa) and [xb1, cr]: the warp walks the rows its lanes own, lanes spread over columns
-        const int nleft = xa - cl, nright = cr + 1 - xb1;
-        for (int l = 0; l < 32; ++l) {
-            const int r2 = l * kProducerWarps + pw;
-            if (r2 >= nrows) break;
-            const float* gp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gp), l));
-            float* drow2 = sm.tile + __shfl_sync(0xffffffffu, ro, l) - cl;
-            const bool zr = __shfl_sync(0xffffffffu, (int)zero_row, l) != 0;      // that row is already all zeros
-            for (int k = lane; k < nleft + nright; k += 32) {
-                const int col = k < nleft ? cl + k : xb1 + (k - nleft);
-                if (im.zero_pad) {
-                    if (!zr) drow2[col] = 0.0f;
-                } else {
-                    cp_async_4(drow2 + col, gp2 + reflect101(col, im.W));
-                }
+        // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels (4-byte cp.async each), or zeros in
+        // zero-padding mode.  All producer threads share the (row, column) pairs; the row table tells where a row sits.
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
+        const int total = nrows * ncols;
+        for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
+            const int r2 = idx / ncols, k = idx - r2 * ncols;
+            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
+            const int irow = rt + r2;
+            float* d = sm.tile + sm.rowtab[r2] - cl + col;
+            if (im.zero_pad) {
+                if (irow >= 0 && irow < im.H) *d = 0.0f;           // rows outside the image are already all zeros
+            } else {
+                cp_async_4(d, plane + (int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W));
             }
         }
     }
