@@ -175,6 +175,20 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+__device__ __forceinline__ uint4 lds_v4u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// eight halves (one 16-byte group) -> eight floats at addr .. addr + 31
+__device__ __forceinline__ void sts_widened(uint32_t addr, const uint4& h8) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h8.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h8.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h8.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&h8.w));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 16u), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y) : "memory");
+}
 
 __device__ __forceinline__ int reflect101(int v, int n) {
     v = v < 0 ? -v : v;
@@ -424,40 +438,25 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
     // bytes of floats.  Within a round of 32 groups the floats land on halves that the round has already read (a float
     // group ends at byte 32 g + 32, the half group it may reach starts at 2 * kPitch + 16 g); rounds ascend along the row.
     {
+        static_assert(kPitch / 8 <= 64, "two rounds of 32 groups cover a staged row");
+        static_assert(kRowsMax * kPitch < (1 << 20), "row offset and group count share one shuffled word");
         const int my_n8 = (in_rows && !zero_row) ? (xb_al - xa_al) >> 3 : 0;
-        const int my_off = ro - cl + xa_al;                                 // float index of the row's first aligned element
-        for (int l = 0; l < 32; ++l) {
-            if (l * kProducerWarps + pw >= nrows) break;
-            const int n8 = __shfl_sync(0xffffffffu, my_n8, l);
-            const int off = __shfl_sync(0xffffffffu, my_off, l);
-            const int r2 = l * kProducerWarps + pw;
-            const float* frow = sm.tile + off;
-            const uint4* hsrc = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(sm.tile + r2 * kPitch) + kPitch +
-                                                               (off - r2 * kPitch));
-            // a row holds at most kPitch / 8 = 60 groups: two rounds, both read before either is written
-            static_assert(kPitch / 8 <= 64, "two rounds of 32 groups cover a staged row");
+        const int packed = (ro - cl + xa_al) | (my_n8 << 20);             // float index of the first aligned element | groups
+        const uint32_t tile_b = smem_u32(sm.tile);
+        uint32_t hb = tile_b + 2u * kPitch * (uint32_t)(pw + 1) + 16u * (uint32_t)lane;     // row pw's halves; + 2 * off
+        const uint32_t fb = tile_b + 32u * (uint32_t)lane;                                    // + 4 * off
+        const int nl = (nrows - pw + kProducerWarps - 1) / kProducerWarps;                   // rows this warp placed
+        for (int l = 0; l < nl; ++l, hb += 2u * kPitch * kProducerWarps) {
+            const int pk = __shfl_sync(0xffffffffu, packed, l);
+            const uint32_t off = (uint32_t)(pk & 0xfffff);
+            const int n8 = pk >> 20;
             const bool g0 = lane < n8, g1 = lane + 32 < n8;
-            uint4 ha = make_uint4(0u, 0u, 0u, 0u), hb = ha;
-            if (g0) ha = hsrc[lane];
-            if (g1) hb = hsrc[lane + 32];
-            __syncwarp();
-            float4* fdst = reinterpret_cast<float4*>(const_cast<float*>(frow)) + 2 * lane;
-            if (g0) {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ha.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ha.y));
-                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&ha.z));
-                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&ha.w));
-                fdst[0] = make_float4(a.x, a.y, b.x, b.y);
-                fdst[1] = make_float4(c.x, c.y, d.x, d.y);
-            }
-            if (g1) {
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hb.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hb.y));
-                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&hb.z));
-                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&hb.w));
-                fdst[64] = make_float4(a.x, a.y, b.x, b.y);
-                fdst[65] = make_float4(c.x, c.y, d.x, d.y);
-            }
+            uint4 ha = make_uint4(0u, 0u, 0u, 0u), hv = ha;
+            if (g0) ha = lds_v4u(hb + 2u * off);
+            if (g1) hv = lds_v4u(hb + 2u * off + 512u);
+            __syncwarp();                                                  // both rounds are read before either is written
+            if (g0) sts_widened(fb + 4u * off, ha);
+            if (g1) sts_widened(fb + 4u * off + 1024u, hv);
         }
         __syncwarp();
     }

@@ -401,6 +401,37 @@ def test_half_io_inside_the_tiled_kernel(dib, shape):
     assert torch.equal(odd, bf.blur_batch([img], ts, [0])[0])
 
 
+def test_edge_inputs(dib):
+    """Empty batches, nothing to blur, channel counts 1 and 4, a one-tap PSF, an all-zero PSF, and an image far larger
+    than the benchmark's (4 x 2100 x 3001: 101 MB, 413 tiles per channel) through size-independent properties."""
+    bf, ops = dib
+    assert bf.blur_batch([], None, []) == []
+    lst = []
+    bf.blur_image_list(lst, [], [])
+    assert lst == []
+    img = torch.rand(3, 70, 90, device="cuda")
+    keep = [img]
+    bf.blur_image_list(keep, [{"blurring": False}], [torch.zeros(1, device="cuda")])
+    assert keep[0] is img                                               # untouched entries keep their identity
+    # a shifted delta moves the image (convolution orientation: the image is read at minus the tap offset)
+    delta = torch.zeros(128, 128, device="cuda")
+    delta[60, 70] = 1.0
+    big = torch.rand(4, 2100, 3001, device="cuda")
+    out = bf.manual_blur(big, delta)
+    assert tuple(out.shape) == (4, 2100, 3001)
+    assert torch.equal(out[:, 10:-10, 10:-10], torch.roll(big, shifts=(-3, 7), dims=(1, 2))[:, 10:-10, 10:-10])
+    one = bf.manual_blur(torch.rand(1, 300, 500, device="cuda"), delta)  # C == 1 comes back 2-D, as .squeeze() leaves it
+    assert tuple(one.shape) == (300, 500)
+    # identity PSF: bit-for-bit the input, on both kernels
+    ident = torch.zeros(128, 128, device="cuda")
+    ident[63, 63] = 1.0
+    assert torch.equal(bf.manual_blur(big, ident), big) and torch.equal(bf.manual_blur(big[:, :200, :300], ident, exact=True), big[:, :200, :300])
+    # an all-zero PSF: the reference divides by a zero sum and blurs with 16384 NaN taps; here the tap capacity check fires
+    from detectinblur_b200 import _lib
+    with pytest.raises(_lib.DibError):
+        ops.compact_taps(torch.zeros(128, 128, device="cuda"), normalize=True)
+
+
 def ts_weights(ts):
     """Dense normalised PSF rebuilt from a tap set (what the oracle's manual_blur takes)."""
     ys, xs, ws = ts.taps(0)

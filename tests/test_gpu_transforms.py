@@ -102,6 +102,27 @@ def test_blur_image_handler_matches_reference_fourier_path(cuda, golden_dir):
         assert (u8 != g["u8_" + name]).mean() < 5e-3, name
 
 
+def test_baseline_config1_cpu_fourier_case_on_the_gpu(cuda):
+    """BASELINE config 1, the reference's own CPU-runnable case: one 640x480 RGB uint8 image from
+    default_rng(0), one PSF from the seeded generator (expl 0.005, low exposure), blurred through BlurImageHandler -- here
+    on the CUDA kernels, against the CPU restatement of the Fourier path (pinned on the reference's outputs)."""
+    from detectinblur_b200.motion_blur import BlurImageHandler
+    from oracle import fourier_oracle as fo
+    arr = np.random.default_rng(0).integers(0, 256, (480, 640, 3)).astype(np.uint8)
+    np.random.seed(1337)
+    random.seed(1337)
+    fraction = random.choice([1 / 18, 1 / 10, 1 / 5])
+    p16, _ = po.stored_psf(0.005, fraction, np.random)
+    psf32 = po.crop128(p16).astype(np.float32)
+    h = BlurImageHandler(None, PSFs=[psf32], pillowImage=Image.fromarray(arr))
+    assert h.blur_image()
+    want_f, want_u8 = fo.fourier_blur(arr, psf32)
+    assert np.abs(h.result[0] - want_f).max() <= 1e-5
+    got_u8 = np.array(h.pilImageResult)
+    assert got_u8.shape == (480, 640, 3) and np.abs(got_u8.astype(int) - want_u8.astype(int)).max() <= 1
+    assert (got_u8 != want_u8).mean() < 5e-3
+
+
 def test_blur_image_handler_errors(cuda):
     from detectinblur_b200.motion_blur import BlurImageHandler
     with pytest.raises(Exception, match="Not correct path"):
