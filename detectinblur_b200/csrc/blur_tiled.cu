@@ -1,27 +1,31 @@
-// Tiled sparse-PSF blur for sm_100a (DIB_ALGO_TILED): the fast path of dib_blur_batch.
+// Tiled sparse-PSF blur for sm_100a (DIB_ALGO_TILED): the fast path of dib_blur_batch (float and half I/O).
 //
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
 // persistent, warp-specialised launch per batch:
 //   * work unit  = one 36 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
 //                  global ticket counter, images with the heaviest PSFs first;
-//   * producer   = one warp.  For every stage (tile x program chunk) it stages tile + halo global -> shared:
-//                  TMA bulk copies (cp.async.bulk, one per tile row, the 16-byte-aligned interior of the row
-//                  segment) plus 4-byte cp.async for the <= 3 unaligned floats at each row end and for all
-//                  reflect-101 border columns, all completing on the stage's "full" mbarrier.  Rows are independent
-//                  copies, so reflected rows cost nothing extra and the reference's native unpitched CHW layout (row
-//                  pitch 5332 B for W = 1333) needs no repacking.  Two stages are in flight; the producer waits on the
-//                  stage's "empty" mbarrier before refilling it;
-//   * consumers  = eight warps (two per SM sub-partition).  Each thread owns a 10-row x 7-column register tile (lanes
-//                  sit 7 floats apart in a row: odd stride -> conflict-free scalar LDS).  Taps are consumed as the
-//                  program built by taps.cu: groups of 4 PSF columns swept row by row; a rotating 11 x 10 register
-//                  window of the input slides with the sweep (the row of the NEXT step is loaded while the current
-//                  step's FMAs issue), so each shared-memory load feeds ~5-14 FMAs and the loop is FP32-pipe bound, not
-//                  LDS bound.  Absent taps inside a group are skipped with warp-uniform branches (70 FMAs each);
+//   * producers  = one warpgroup (4 warps, 56 registers after setmaxnreg.dec).  For every stage (tile x program chunk)
+//                  thread t stages row t of tile + halo global -> shared: one TMA bulk copy (cp.async.bulk) for the
+//                  16-byte-aligned interior of the row segment, 4-byte cp.async for the <= 3 unaligned floats at each
+//                  row end and, shared out over all producer threads, for the reflect-101 border columns, all completing
+//                  on the stage's "full" mbarrier.  Rows are independent copies, so reflected rows cost nothing extra
+//                  and the reference's native unpitched CHW layout (row pitch 5332 B for W = 1333) needs no repacking;
+//                  a row table records each row's 0-3 float skew.  Two stages are in flight; a refill waits on the
+//                  stage's "empty" mbarrier.  Half-precision images: the rows land as halves in the second half of
+//                  their own bytes and the producer warps widen them in place (issue_stage_half);
+//   * consumers  = twelve warps (6 x 2 over the tile, three per SM sub-partition, 152 registers after
+//                  setmaxnreg.inc).  Each thread owns a 6-row x 7-column output block (lanes sit 7 floats apart in a
+//                  row: odd stride -> conflict-free scalar LDS); rows r and r + 3 share 64-bit accumulators and every
+//                  multiply-add is a packed FFMA2.  Taps are consumed as the program built by taps.cu: groups of 4 PSF
+//                  columns swept row by row; a rotating 6 x 10 register window of the input slides with the sweep
+//                  (one new row per step, loaded into the slot the previous step freed, consumed last).  Absent taps
+//                  inside a group are skipped with warp-uniform branches (21 FFMA2 each);
 //   * epilogue   = noise / clamp / gamma / (x - mean) / std (blur_functions.py:72-74, net_transforms.py:135-139) fused
 //                  on the way out, per warp and without block-level barriers: accumulators -> the warp's private
-//                  row buffer (skewed to the global address phase) -> 16-byte vector stores, scalar stores only for
-//                  the <= 3 unaligned floats at each row end.
+//                  two-row buffer -> 16-byte vector stores.  Destinations with 16-byte-aligned rows take a lean store;
+//                  others stage each row skewed to its global address phase and store the <= 3 unaligned floats at
+//                  each row end one by one.
 // No tensor cores: the contraction is sparse and data dependent.  Results differ from the exact-order kernel only
 // by FMA contraction and tap order (measured <= 4e-7 on [0,1] images; bound 1e-5).
 #include "dib_common.cuh"

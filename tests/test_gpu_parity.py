@@ -128,7 +128,7 @@ def test_reflect_needs_side_above_64(dib):
 
 @pytest.mark.parametrize("shape", [(3, 200, 300), (3, 81, 225), (1, 65, 449), (4, 161, 230), (3, 480, 640)])
 def test_tiled_vs_oracle_seeded(dib, shape):
-    """Sizes the oracle finishes in seconds; odd shapes straddle tile (80 x 224) boundaries."""
+    """Sizes the oracle finishes in seconds; odd shapes straddle tile (36 x 448) and warp-block (6 x 224) boundaries."""
     bf, ops = dib
     rng = np.random.default_rng(sum(shape))
     img = rng.random(shape, dtype=np.float32)
