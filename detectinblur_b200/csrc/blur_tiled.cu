@@ -299,7 +299,8 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
 // right image border then get their reflect-101 columns, each warp covering the rows its own lanes placed.  In
 // zero-padding mode rows and columns outside the image are stored as zeros instead (plain shared-memory stores, which
 // the thread's own arrive on the stage barrier publishes to the consumers).
-__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar, int pt) {
+__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar, int pt,
+                                            uint64_t* empty_bar, uint32_t empty_parity, bool wait_empty) {
     const TiledImage& im = p.img[st.img];
     const int lane = pt & 31, pw = pt >> 5;
     const int sr = lane * kProducerWarps + pw;                             // rows interleave over the producer warps
@@ -309,6 +310,26 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;            // last staged image column
     const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;              // in-image part [xa, xb1)
     const float* plane = static_cast<const float*>(im.src) + (int64_t)st.ch * im.src_cp;
+    // Where this thread's row comes from and where it goes: pure arithmetic, done before the wait for the buffer so that
+    // the copies go out as soon as the consumers release it.
+    const float* gp = plane;
+    int ro = sr * kPitch;
+    int xa_al = cl, xb_al = cl;              // nothing inside the image: every column is mirrored
+    const bool in_rows = sr < nrows;
+    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
+    if (in_rows && !zero_row) {
+        gp = plane + (int64_t)reflect101(rt + sr, im.H) * im.src_rp;
+        if (xb1 > xa) {
+            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 2);
+            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 3u);
+            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 3u);
+            if (xb_al <= xa_al) xa_al = xb_al = xa;      // segment shorter than one aligned quad
+        }
+        ro += (int)((uint32_t)(cl - xa_al) & 3u);       // skew: makes (xa_al - cl + skew) a multiple of 4
+    }
+    float* drow = sm.tile + ro - cl;                     // drow[col] addresses image column col
+    const uint32_t nb_row = (in_rows && !zero_row) ? (uint32_t)(xb_al - xa_al) * 4u : 0u;
+    if (wait_empty) mbar_wait(empty_bar, empty_parity);  // consumers released the stage that used this buffer
     fence_proxy_async();   // order the consumers' generic-proxy reads of this buffer before the async-proxy writes
     if (pt == 0) {
         StageHdr h;
@@ -318,30 +339,11 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
         *sm.hdr = h;
     }
-    uint32_t bytes = 0;
-    const float* gp = plane;
-    int ro = sr * kPitch;
-    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
-    if (sr < nrows && zero_row) {
-        float* drow = sm.tile + ro - cl;
+    uint32_t bytes = nb_row;
+    if (in_rows && zero_row) {
         for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
-    } else if (sr < nrows) {
-        const int srow = reflect101(rt + sr, im.H);
-        gp = plane + (int64_t)srow * im.src_rp;
-        int xa_al = cl, xb_al = cl;          // nothing inside the image: every column is mirrored
-        if (xb1 > xa) {
-            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 2);
-            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 3u);
-            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 3u);
-            if (xb_al <= xa_al) xa_al = xb_al = xa;      // segment shorter than one aligned quad
-        }
-        ro += (int)((uint32_t)(cl - xa_al) & 3u);       // skew: makes (xa_al - cl + skew) a multiple of 4
-        float* drow = sm.tile + ro - cl;                 // drow[col] addresses image column col
-        const uint32_t nb = (uint32_t)(xb_al - xa_al) * 4u;
-        if (nb) {
-            tma_bulk_g2s(drow + xa_al, gp + xa_al, nb, bar);
-            bytes += nb;
-        }
+    } else if (in_rows) {
+        if (nb_row) tma_bulk_g2s(drow + xa_al, gp + xa_al, nb_row, bar);
         for (int col = xa; col < xa_al; ++col) cp_async_4(drow + col, gp + col);      // unaligned head
         for (int col = xb_al; col < xb1; ++col) cp_async_4(drow + col, gp + col);     // unaligned tail
     }
@@ -914,7 +916,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         for (int n = 0;; ++n) {
             const int b = n & 1;
             next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the issue below
-            if (n >= 2) mbar_wait(&empty[b], ((n >> 1) - 1) & 1);    // consumers released the stage that used this buffer
+            const bool wait_empty = n >= 2;
+            const uint32_t empty_parity = (uint32_t)(((n >> 1) - 1) & 1);
+            // the float path waits inside issue_stage, after the row arithmetic
+            if ((kHalf || cur.tile < 0) && wait_empty) mbar_wait(&empty[b], empty_parity);
             const StageSmem sm = stage_smem(smem, b);
             if (cur.tile < 0) {
                 if (pt == 0) sm.hdr->tile = -1;
@@ -938,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             if constexpr (kHalf)
                 issue_stage_half(p, cur, sm, &landed[b], (uint32_t)((n >> 1) & 1), &full[b], pt);
             else
-                issue_stage(p, cur, sm, &full[b], pt);
+                issue_stage(p, cur, sm, &full[b], pt, &empty[b], empty_parity, wait_empty);
             cur = nxt;
         }
     } else {
