@@ -179,19 +179,16 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
-__device__ __forceinline__ uint4 lds_v4u(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+__device__ __forceinline__ uint2 lds_v2u(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
-// eight halves (one 16-byte group) -> eight floats at addr .. addr + 31
-__device__ __forceinline__ void sts_widened(uint32_t addr, const uint4& h8) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h8.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h8.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h8.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&h8.w));
+// four halves (8 bytes) -> four floats at addr .. addr + 15
+__device__ __forceinline__ void sts_widened(uint32_t addr, const uint2& h4) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h4.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h4.y));
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 16u), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y) : "memory");
 }
 
 __device__ __forceinline__ int reflect101(int v, int n) {
@@ -444,25 +441,31 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
     // bytes of floats.  Within a round of 32 groups the floats land on halves that the round has already read (a float
     // group ends at byte 32 g + 32, the half group it may reach starts at 2 * kPitch + 16 g); rounds ascend along the row.
     {
-        static_assert(kPitch / 8 <= 64, "two rounds of 32 groups cover a staged row");
+        static_assert(kPitch / 4 <= 128, "four chunks per lane cover a staged row");
         static_assert(kRowsMax * kPitch < (1 << 20), "row offset and group count share one shuffled word");
         const int my_n8 = (in_rows && !zero_row) ? (xb_al - xa_al) >> 3 : 0;
         const int packed = (ro - cl + xa_al) | (my_n8 << 20);             // float index of the first aligned element | groups
+        // A lane widens four 4-element chunks per row, 32 chunks apart: every load (8 bytes per lane) and every store (16
+        // bytes per lane) of the warp covers one contiguous span, so neither has bank conflicts.
         const uint32_t tile_b = smem_u32(sm.tile);
-        uint32_t hb = tile_b + 2u * kPitch * (uint32_t)(pw + 1) + 16u * (uint32_t)lane;     // row pw's halves; + 2 * off
-        const uint32_t fb = tile_b + 32u * (uint32_t)lane;                                    // + 4 * off
+        uint32_t hb = tile_b + 2u * kPitch * (uint32_t)(pw + 1) + 8u * (uint32_t)lane;      // row pw's halves; + 2 * off
+        const uint32_t fb = tile_b + 16u * (uint32_t)lane;                                    // + 4 * off
         const int nl = (nrows - pw + kProducerWarps - 1) / kProducerWarps;                   // rows this warp placed
         for (int l = 0; l < nl; ++l, hb += 2u * kPitch * kProducerWarps) {
             const int pk = __shfl_sync(0xffffffffu, packed, l);
             const uint32_t off = (uint32_t)(pk & 0xfffff);
-            const int n8 = pk >> 20;
-            const bool g0 = lane < n8, g1 = lane + 32 < n8;
-            uint4 ha = make_uint4(0u, 0u, 0u, 0u), hv = ha;
-            if (g0) ha = lds_v4u(hb + 2u * off);
-            if (g1) hv = lds_v4u(hb + 2u * off + 512u);
-            __syncwarp();                                                  // both rounds are read before either is written
-            if (g0) sts_widened(fb + 4u * off, ha);
-            if (g1) sts_widened(fb + 4u * off + 1024u, hv);
+            const int n4 = (pk >> 20) * 2;                                  // 4-element chunks of the row (<= 120)
+            const uint32_t h0 = hb + 2u * off, f0 = fb + 4u * off;
+            uint2 hv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hv[j] = make_uint2(0u, 0u);
+                if (lane + 32 * j < n4) hv[j] = lds_v2u(h0 + 256u * j);
+            }
+            __syncwarp();                                                  // the whole row is read before any of it is written
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane + 32 * j < n4) sts_widened(f0 + 512u * j, hv[j]);
         }
         __syncwarp();
     }
