@@ -14,6 +14,11 @@ DIB_F32, DIB_F16, DIB_F64 = 0, 1, 2
 PAD_REFLECT128, PAD_ZERO128, PAD_REPLICATE256 = 0, 1, 2
 EPI_NOISE, EPI_CLAMP, EPI_GAMMA, EPI_NORMALIZE, EPI_PHILOX = 1, 2, 4, 8, 16
 ALGO_AUTO, ALGO_GENERIC, ALGO_TILED = 0, 1, 2
+ALGO_OVERLAP = 0x100
+
+
+def algo_slot(k):
+    return (k & 3) << 12
 META_TRUNCATED, META_NO_PROGRAM = 1, 2
 MAX_BATCH = 32
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY = -1, -2, -3, -4

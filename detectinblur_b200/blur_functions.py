@@ -65,7 +65,10 @@ class BlurPlan(object):
         self.philox_seed, self.device, self.results, self._keep = philox_seed, device, results, keep
         self._launches = ctypes.c_int(0)
 
-    def run(self):
+    def run(self, overlap=False):
+        """Launch.  ``overlap=True`` declares this batch independent of whatever was launched just before it on the
+        stream (e.g. the previous batch of a loop over independent batches): the kernel may then start on SMs that launch
+        has already vacated instead of waiting for its last tile.  Chunks of one oversized batch always overlap."""
         global _launch_count
         ts = self.tapset
         with torch.cuda.device(self.device):
@@ -73,9 +76,15 @@ class BlurPlan(object):
             for lo in range(0, self.n, _lib.MAX_BATCH):
                 cnt = min(_lib.MAX_BATCH, self.n - lo)
                 sub = ctypes.cast(ctypes.byref(self.descs, lo * ctypes.sizeof(_lib.Image)), ctypes.POINTER(_lib.Image))
+                algo = self.algo
+                if ts is not None:
+                    ts.launch_seq = getattr(ts, "launch_seq", 0) + 1      # overlapping launches rotate scheduler slots
+                    algo |= _lib.algo_slot(ts.launch_seq)
+                    if overlap or lo > 0:
+                        algo |= _lib.ALGO_OVERLAP
                 _lib.check(_lib.lib.dib_blur_batch(sub, cnt, ctypes.c_void_p(ts.buffer.data_ptr()) if ts is not None else None,
                                                    ts.n_psfs if ts is not None else 0, ts.max_taps if ts is not None else 0,
-                                                   ts.meta if ts is not None else None, _DT[self.dtype], self.algo,
+                                                   ts.meta if ts is not None else None, _DT[self.dtype], algo,
                                                    int(self.philox_seed or 0), lo, ctypes.byref(self._launches), stream))
                 _launch_count += self._launches.value
         return self.results
@@ -206,7 +215,7 @@ class _HalfPlan(object):
         self.kw = dict(noise=None if noise is None else [None if z is None else z.float() for z in noise], noise_sd=noise_sd,
                        clamp=clamp, philox_seed=philox_seed, mean=mean, std=std, gamma=gamma, exact=False, pad_mode=pad_mode)
 
-    def run(self):
+    def run(self, overlap=False):
         wide = [im.float() for im in self.images]
         res32 = prepare_blur(wide, self.tapset, self.psf_indices, **self.kw).run()
         results = []

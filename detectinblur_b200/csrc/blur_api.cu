@@ -9,7 +9,7 @@ namespace dib {
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
                    int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, cudaStream_t st);
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st);
 
 static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
     if (meta_host == nullptr || im.psf_index < 0) return false;
@@ -37,6 +37,10 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     DIB_CHECK_ARG(images != nullptr, "dib_blur_batch: images is NULL");
     DIB_CHECK_ARG(n_images >= 0 && n_images <= DIB_MAX_BATCH, "dib_blur_batch: n_images %d outside [0, %d]", n_images, DIB_MAX_BATCH);
     DIB_CHECK_ARG(io_dtype == DIB_F32 || io_dtype == DIB_F16, "dib_blur_batch: io_dtype must be DIB_F32 or DIB_F16");
+    const bool overlap_prev = (algo & DIB_ALGO_OVERLAP) != 0;
+    const int sched_slot = (algo >> 12) & 3;
+    DIB_CHECK_ARG((algo & ~(0xff | DIB_ALGO_OVERLAP | DIB_ALGO_SLOT(3))) == 0, "dib_blur_batch: unknown algo flags 0x%x", algo);
+    algo &= 0xff;
     DIB_CHECK_ARG(algo == DIB_ALGO_AUTO || algo == DIB_ALGO_GENERIC || algo == DIB_ALGO_TILED, "dib_blur_batch: unknown algo %d", algo);
     if (n_images == 0) return DIB_OK;
     bool any_psf = false;
@@ -65,7 +69,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     const dib_psf_meta* meta_dev = reinterpret_cast<const dib_psf_meta*>(base + L.meta_offset);
     const dib_tap* taps = reinterpret_cast<const dib_tap*>(base + L.taps_offset);
     const uint8_t* prog = base + L.prog_offset;
-    SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset);
+    SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset) + sched_slot;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     // split the batch: tiled kernel where eligible (heaviest PSFs first), exact-order kernel for the rest
@@ -97,7 +101,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     }
     int nl = 0;
     if (n_sel > 0) {
-        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, io_dtype, st);
+        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, io_dtype, overlap_prev, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

@@ -115,6 +115,7 @@ struct TiledParams {
     int total_tiles;
     uint64_t philox_seed, philox_offset;
     SchedWords* sched;            // dynamic tile scheduler (tap set buffer): tiles are handed out in index order
+    int overlap_prev;             // DIB_ALGO_OVERLAP: do not wait for the grid launched before this one
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -890,6 +891,12 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     int* tile_slots = reinterpret_cast<int*>(bars + 6);
     const int warp = threadIdx.x >> 5;
 
+    // Programmatic dependent launch: let the next launch on the stream start filling SMs as this grid's CTAs retire, and
+    // -- unless the caller declared this batch independent of the previous launch -- wait for that launch to complete
+    // (and flush) before touching global memory.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
+
     if (threadIdx.x == 0) {
         // float: per producer thread one arrive.expect_tx + one cp.async arrive; half: one plain arrive after widening
         mbar_init(&full[0], (kHalf ? 1 : 2) * kProducerWarps * 32);
@@ -993,7 +1000,7 @@ int tiled_tile_counts(int H, int W, int* tiles_y, int* tiles_x) {
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, cudaStream_t st) {
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st) {
     static thread_local int sm_count = 0;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
@@ -1049,22 +1056,35 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_seed = seed;
     p.philox_offset = offset;
     p.sched = sched;
+    p.overlap_prev = overlap_prev ? 1 : 0;
     const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
+    // launched with the programmatic-stream-serialization attribute: the kernel itself decides (griddepcontrol.wait)
+    // whether it orders itself after the previous launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (io_dtype == DIB_F16) {
         if (any_general) {
             set_error("dib_blur_batch: half images with a noise / clamp / gamma epilogue do not take the tiled kernel");
             return DIB_ERR_UNSUPPORTED;
         }
         if (any_epi)
-            blur_tiled_kernel<kEpiAffine, true><<<grid, kThreads, kSmemBytes, st>>>(p);
+            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, true>, p));
         else
-            blur_tiled_kernel<kEpiNone, true><<<grid, kThreads, kSmemBytes, st>>>(p);
+            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, true>, p));
     } else if (any_general) {
-        blur_tiled_kernel<kEpiGeneral, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiGeneral, false>, p));
     } else if (any_epi) {
-        blur_tiled_kernel<kEpiAffine, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, false>, p));
     } else {
-        blur_tiled_kernel<kEpiNone, false><<<grid, kThreads, kSmemBytes, st>>>(p);
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, false>, p));
     }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;

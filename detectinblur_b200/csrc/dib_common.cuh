@@ -70,6 +70,8 @@ struct SchedWords {
     unsigned int next_tile;     // next tile to hand out
     unsigned int done_ctas;     // CTAs that have stopped fetching
 };
+constexpr int kSchedSlots = 4;      // launches that may overlap (DIB_ALGO_OVERLAP) rotate through these (256 bytes are reserved)
+
 
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 

@@ -132,8 +132,10 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
 
     const int n = blockIdx.x;
     if (n == 0 && threadIdx.x == 0) {
-        sched->next_tile = 0u;
-        sched->done_ctas = 0u;
+        for (int k = 0; k < kSchedSlots; ++k) {
+            sched[k].next_tile = 0u;
+            sched[k].done_ctas = 0u;
+        }
     }
     const T* psf = psfs + (int64_t)n * psf_stride;
     const int cells = side * side;

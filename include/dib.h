@@ -119,6 +119,13 @@ typedef struct dib_image {
 #define DIB_ALGO_GENERIC 1    /* exact-order kernel: per tap one rounded multiply and one rounded add, bit-identical
                                  to the reference loop for fp32 and fp16 */
 #define DIB_ALGO_TILED 2      /* fail instead of falling back */
+/* Flags OR-ed into `algo`.  DIB_ALGO_OVERLAP: the caller asserts that this batch does not depend on the work launched just
+ * before it on the stream (typically the previous, independent batch), so the tiled kernel may start on SMs that kernel has
+ * already vacated (programmatic dependent launch: its tail overlaps this launch's ramp-up) instead of waiting for the whole
+ * grid.  Launches that may overlap and share a tap set must use different scheduler slots: DIB_ALGO_SLOT(k), k = a launch
+ * counter modulo 4.  Without the flag a launch is ordered after everything before it on the stream, as usual. */
+#define DIB_ALGO_OVERLAP 0x100
+#define DIB_ALGO_SLOT(k) (((k) & 3) << 12)
 
 DIB_API int dib_abi_version(void);
 DIB_API const char* dib_last_error(void);
