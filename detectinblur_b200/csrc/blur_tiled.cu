@@ -265,7 +265,9 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
 __device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int& nfetch, int pt) {
     int* slot = slots + (nfetch & 1);
     if (pt == 0) {
-        const unsigned t = atomicAdd(&p.sched->next_tile, 1u);
+        // the first tile of a CTA is its block index (no round trip to the counter before the first load can go out);
+        // tickets from the counter follow after the gridDim.x tiles handed out that way
+        const unsigned t = nfetch == 0 ? blockIdx.x : gridDim.x + atomicAdd(&p.sched->next_tile, 1u);
         *slot = t < (unsigned)p.total_tiles ? (int)t : -1;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
