@@ -309,6 +309,19 @@ def run_own_arm(args, spec):
         elapsed_ms = float(t.item())
     value = world * B * args.steps / (elapsed_ms / 1000.0)
 
+    # the same steps with every launch ordered after the previous one, for reference (not the reported value)
+    ordered_ms = None
+    if overlap:
+        n_ord = max(10, min(args.steps, 200))
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        o0.record()
+        for k in range(n_ord):
+            plans[k % n_rot].run(overlap=False)
+        o1.record()
+        torch.cuda.synchronize()
+        ordered_ms = o0.elapsed_time(o1) / n_ord
+
     # ---- kernel duration, live: the K blur launches are the only work between the two events: average per launch
     kern_ms = float(per_step.mean())
     algo_bytes = ALGO_BYTES_PER_IMAGE * B * esize // 4
@@ -431,6 +444,7 @@ def run_own_arm(args, spec):
                        "step_overlap": ("consecutive steps are independent batches (own inputs, own outputs) launched with "
                                         "programmatic dependent launch: the tail of step k overlaps the ramp-up of step k + 1"
                                         if overlap else "every step is ordered after the previous one"),
+                       "ms_per_step_ordered": ordered_ms,
                        "output_layout": "rows 16-byte aligned (pitch %d floats), returned as [:, :, :W] views" % outs.shape[3],
                        "l2": "3 rotating input batches (3 x %.0f MB in, %.0f MB out) > 126 MB L2" % (
                            B * C * H * W * esize / 1e6, B * C * H * W * esize / 1e6),
