@@ -196,26 +196,36 @@ def run_reference_arm(args, spec):
     pool = mp.get_context("spawn").Pool(cores)
     pool.map(_cpu_worker, [(k, 0, psf) for k in range(cores)])
     per_core = max(1, -(-spec["batch"] // cores))        # a step = one batch spread over the host cores
-    for _ in range(args.warmup):
+    # A step costs ~0.5 s of all host cores, so K and W are honoured up to a wall-clock budget: the run always ends within
+    # a couple of minutes, whatever K the caller passes (the own arm's K is sized for 60-us steps).
+    budget_s = float(os.environ.get("DIB_REFERENCE_BUDGET_S", "90"))
+    t_start = time.perf_counter()
+    for _ in range(min(args.warmup, 2)):
         cpu_fourier_throughput(psf, per_core, pool, cores)
     t0 = time.perf_counter()
     n_img = 0
+    steps_timed = 0
     for _ in range(args.steps):
         cpu_fourier_throughput(psf, per_core, pool, cores)
         n_img += per_core * cores
+        steps_timed += 1
+        if steps_timed >= 3 and time.perf_counter() - t_start > budget_s:
+            break
     wall = time.perf_counter() - t0
     pool.close()
     pool.join()
     value = n_img / wall
     line = {
         "impl": "reference", "metric": "blurred images/sec (800x1333 RGB)", "value": value, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "steps_timed": steps_timed, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * wall / steps_timed,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": spec["desc"], "path": "CPU Fourier blur (motion_blur/blur_image.py port, --cpu_blur)",
                    "images_per_step": per_core * cores},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d images of 800x1333x3 uint8, one process per core, scipy fftconvolve" % (
-                             args.steps, per_core * cores)},
+                         "sample": "%d steps x %d images of 800x1333x3 uint8 (%.0f s; a %d-step request is cut at a %.0f s budget), "
+                                   "one process per core, scipy fftconvolve" % (steps_timed, per_core * cores, wall, args.steps,
+                                                                                budget_s)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
