@@ -1,3 +1,8 @@
+"""A small end-to-end case for compute-sanitizer runs (not collected by pytest):
+
+    compute-sanitizer --tool memcheck python tests/sanitize_case.py
+
+Lives under tests/ because it draws its PSFs with the oracle (test infrastructure)."""
 import torch, numpy as np, sys
 sys.path.insert(0, ".")
 import detectinblur_b200.blur_functions as bf, detectinblur_b200.psf_ops as ops
