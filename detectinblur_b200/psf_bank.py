@@ -128,7 +128,7 @@ class PackedPsfBank(object):
 
     def _folder_packs(self, param_index, fraction_index):
         key = (param_index, fraction_index)
-        if key not in self._packs:
+        if not self._packs.get(key):              # an empty result is not cached: packs may be written later
             stem = os.path.join(self.directory, "P" + str(param_index) + "E" + str(fraction_index))
             self._packs[key] = [_Pack(p) for p in sorted(glob.glob(stem + ".dibpack") + glob.glob(stem + ".w*.dibpack"))]
         return self._packs[key]
