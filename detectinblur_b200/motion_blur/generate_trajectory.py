@@ -6,9 +6,6 @@ inherently sequential host work and the seeded samples are the INPUT of the GPU 
 (psf_ops.rasterize_psfs), exactly as BASELINE.json's north_star lays out.  Same constructor, attributes and
 RNG consumption as the reference class, so a seeded run yields bit-identical ``x``.
 """
-import cmath
-import math
-
 import numpy as np
 
 

@@ -22,7 +22,6 @@ import random
 import numpy as np
 import torch
 
-from . import blur_functions
 from . import psf_bank
 from . import psf_ops
 from .motion_blur.generate_trajectory import Trajectory
