@@ -103,6 +103,8 @@ struct TiledImage {
     int epilogue;
     int zero_pad;         // DIB_PAD_ZERO128: pixels outside the image read as 0 instead of being mirrored
     int aligned_out;      // every destination row starts 16-byte aligned (base, row pitch and channel pitch): lean row store
+    int rec0_valid;       // single-chunk PSF: its one chunk record, rebuilt on the host from the PSF summary, rides in the
+    ChunkRec rec0;        // kernel parameters, so a tile's first stage need not wait for a load from the program section
     int philox_slot;      // position in the caller's batch (Philox stream id)
     float noise_sd, gamma;
     float mean[4], std[4];
@@ -247,6 +249,7 @@ __device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stag
 }
 
 __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img, int chunk) {
+    if (p.img[img].rec0_valid) return p.img[img].rec0;          // single-chunk PSF (chunk == 0)
     const uint8_t* prog = p.prog + (size_t)p.img[img].psf_index * kProgBytes;
     const int4 v = __ldg(reinterpret_cast<const int4*>(prog) + chunk);
     ChunkRec r;
@@ -1039,6 +1042,21 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.nchunks = m.prog_chunks;
         t.epilogue = im.epilogue;
         t.zero_pad = (im.pad_mode == DIB_PAD_ZERO128);
+        // A PSF whose program is one chunk: taps.cu builds that chunk from the support's bounding box alone (first group at
+        // xmin, rows ymin .. ymax, data right after the chunk table), so the record is reproduced here from the host summary.
+        t.rec0_valid = 0;
+        if (m.prog_chunks == 1) {
+            const int centre = 63;
+            const int g_last = (m.xmax - m.xmin) / kGroupW;
+            t.rec0.dy_lo = (int16_t)(m.ymin - centre);
+            t.rec0.dy_hi = (int16_t)(m.ymax - centre);
+            t.rec0.dx_lo = (int16_t)(m.xmin - centre);
+            t.rec0.dx_hi = (int16_t)(m.xmin - centre + g_last * kGroupW + kGroupW - 1);
+            t.rec0.nseg = (int16_t)m.prog_segs;
+            t.rec0.wsteps = (int16_t)m.prog_steps;
+            t.rec0.data_off = (int32_t)kProgHeaderBytes;
+            t.rec0_valid = 1;
+        }
         t.aligned_out = ((reinterpret_cast<uintptr_t>(im.dst) & 15u) == 0 && (im.dst_row_pitch & 3) == 0 && (im.dst_chan_pitch & 3) == 0) ? 1 : 0;
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
         any_epi |= (t.epilogue != 0);

@@ -459,6 +459,25 @@ def test_overlapped_launches_of_independent_batches(dib):
     assert all(torch.equal(a, b) for a, b in zip(again, want[0]))
 
 
+def test_many_single_chunk_psfs_tiled_vs_exact(dib):
+    """Low-exposure PSFs fit one program chunk; for those the kernel takes the chunk record from its parameters (rebuilt on
+    the host from the PSF summary) instead of loading it.  30 different PSFs, tiled against the exact-order kernel."""
+    bf, ops = dib
+    np.random.seed(2024)
+    psfs = []
+    for k in range(30):
+        p16, _ = po.stored_psf([0.005, 0.001, 0.00005][k % 3], [1 / 18, 1 / 10, 1 / 5][k % 3 if k < 15 else (k + 1) % 3], np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    ts = ops.compact_taps(_cuda(np.stack(psfs)), normalize=True)
+    assert sum(1 for m in ts.meta if m.prog_chunks == 1) >= 20
+    gen = torch.Generator().manual_seed(9)
+    imgs = [torch.rand((3, 100 + 7 * (k % 5), 470 + 11 * (k % 4)), generator=gen).cuda() for k in range(30)]
+    fast = bf.blur_batch(imgs, ts, list(range(30)))
+    exact = bf.blur_batch(imgs, ts, list(range(30)), exact=True)
+    for a, b in zip(fast, exact):
+        assert (a - b).abs().max().item() <= TOL_FP32
+
+
 def ts_weights(ts):
     """Dense normalised PSF rebuilt from a tap set (what the oracle's manual_blur takes)."""
     ys, xs, ws = ts.taps(0)
