@@ -172,3 +172,46 @@ def test_trajectory_mirror_bit_exact(golden_dir):
         tr = Trajectory(canvas=256, max_len=96, expl=expl).fit().fit()
         assert np.array_equal(tr.x, g["x_%d" % k]), k
         assert tr.x.dtype == np.complex128 and len(tr.x) == 2000
+
+
+def test_host_rules_without_a_gpu():
+    """Pure host logic of the mirrors: boundary-mode rule, resize scale / padded batch extent, fp16 fast-path gate."""
+    import torch
+    from detectinblur_b200 import _lib
+    from detectinblur_b200 import blur_functions as bf
+    from detectinblur_b200 import net_transforms as nt
+    from oracle import resize_oracle as ro
+    # manual_blur's boundary rule (blur_functions.py:17, :55-58): zeros below 64 px, reflect above, 64 itself raises
+    assert bf.pad_mode_for(128, 63, 500) == _lib.PAD_ZERO128 and bf.pad_mode_for(128, 500, 40) == _lib.PAD_ZERO128
+    assert bf.pad_mode_for(128, 65, 65) == _lib.PAD_REFLECT128 and bf.pad_mode_for(256, 65, 65) == _lib.PAD_REPLICATE256
+    for hw in ((64, 500), (500, 64)):
+        with pytest.raises(RuntimeError, match="Padding size should be less"):
+            bf.pad_mode_for(128, *hw)
+    # resize scale and padded extent (net_transforms.py:36-48, :236-247)
+    for h, w in ((480, 640), (640, 427), (800, 1333), (333, 500), (1200, 300)):
+        assert nt.resize_scale(h, w, 800, 1333) == ro.resize_scale(h, w, 800, 1333)
+    assert nt.padded_batch_shape([(800, 1333), (750, 1000)]) == (800, 1344)
+    assert nt.padded_batch_shape([(97, 131)]) == (128, 160)
+
+    # the gate of the in-kernel half path: only the normalize epilogue, aligned destinations, sides > 64, a tiled program
+    class Meta(object):
+        def __init__(self, count=20, chunks=1, flags=0):
+            self.count, self.prog_chunks, self.flags = count, chunks, flags
+
+    class Ts(object):
+        side = 128
+        meta = [Meta(), Meta(flags=_lib.META_NO_PROGRAM), Meta(count=0)]
+
+    img = torch.zeros((3, 100, 131), dtype=torch.float16)
+    ok = lambda **kw: bf._half_tiled_ok(kw.pop("images", [img]), Ts(), kw.pop("idx", [0]), kw.pop("outs", None), kw.pop("noise", None),
+                                        kw.pop("noise_sd", None), kw.pop("clamp", None), kw.pop("philox_seed", None),
+                                        kw.pop("gamma", None), kw.pop("pad_mode", None))
+    assert ok()
+    assert ok(pad_mode=_lib.PAD_ZERO128) and not ok(pad_mode=_lib.PAD_REPLICATE256)
+    assert not ok(idx=[1]) and not ok(idx=[2]) and not ok(idx=[-1])
+    assert not ok(clamp=[False]) and not ok(noise_sd=[0.1]) and not ok(gamma=[2.2]) and not ok(philox_seed=1)
+    assert not ok(images=[torch.zeros((3, 64, 131), dtype=torch.float16)])
+    assert not ok(images=[img.float()])
+    aligned = torch.zeros((3, 100, 136), dtype=torch.float16)[:, :, :131]
+    assert ok(outs=[aligned]) and not ok(outs=[torch.zeros((3, 100, 132), dtype=torch.float16)[:, :, 1:]])
+    assert not ok(outs=[aligned.float()])
