@@ -478,6 +478,24 @@ def test_many_single_chunk_psfs_tiled_vs_exact(dib):
         assert (a - b).abs().max().item() <= TOL_FP32
 
 
+def test_half_io_full_size(dib):
+    """BASELINE's full size in fp16 (3 x 800 x 1333: odd width, rows at every 2-byte phase, border tiles on all sides):
+    the in-kernel half path against torch casts around the fp32 kernel, plain and with the fused normalize."""
+    bf, ops = dib
+    gen = torch.Generator().manual_seed(5)
+    imgs = [torch.rand((3, 800, 1333), generator=gen).half().cuda() for _ in range(2)]
+    np.random.seed(11)
+    psfs = [po.crop128(po.stored_psf(e, f, np.random)[0]) for e, f in ((0.005, 1 / 5), (0.00005, 1))]
+    ts = ops.compact_taps(_cuda(np.stack(psfs)), normalize=True)
+    fused = bf.blur_batch(imgs, ts, [0, 1])
+    casts = bf.blur_batch(imgs, ts, [0, 1], clamp=[False, False])
+    assert all(torch.equal(a, b) for a, b in zip(fused, casts))
+    mean, std = [[0.485, 0.456, 0.406]] * 2, [[0.229, 0.224, 0.225]] * 2
+    n16 = bf.blur_batch(imgs, ts, [0, 1], mean=mean, std=std)
+    n32 = bf.blur_batch([i.float() for i in imgs], ts, [0, 1], mean=mean, std=std)
+    assert max((a.float() - b).abs().max().item() for a, b in zip(n16, n32)) <= 4e-3
+
+
 def ts_weights(ts):
     """Dense normalised PSF rebuilt from a tap set (what the oracle's manual_blur takes)."""
     ys, xs, ws = ts.taps(0)
