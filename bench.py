@@ -434,7 +434,13 @@ def run_own_arm(args, spec):
                    "sample": "%d images of 800x1333x3 (%d per core, one process per core), CPU Fourier blur port "
                              "(oracle/fourier_oracle.py), %.1f s wall" % (cores * per_core, per_core, wall)}
         # the roofline leg that binds this workload: bytes at HBM peak vs taps x pixels FMAs at the FP32 peak
-        common = {"traffic": traffic, "kernel": "dib::blur_tiled_kernel", "kernel_ms": kern_ms,
+        # kernel_ms is the average time per launch inside the timed region, where consecutive launches overlap tail-to-head;
+        # kernel_ms_ordered / frac_ordered are the same quantities with every launch ordered after the previous one
+        ordered = {}
+        if ordered_ms is not None:
+            ordered = {"kernel_ms_ordered": ordered_ms,
+                       "frac_ordered": max(t_hbm, t_fma) / (ordered_ms * 1e-3)}
+        common = {"traffic": traffic, "kernel": "dib::blur_tiled_kernel", "kernel_ms": kern_ms, **ordered,
                   "algorithmic_bytes_per_launch": algo_bytes, "fma_per_launch": fmas, "fp32_probe_tflops": fp32_tflops,
                   "hbm_peak_gbs": hbm_peak, "t_hbm_ms": t_hbm * 1e3, "t_fp32_ms": t_fma * 1e3,
                   "frac_of_max_roofline": roof_frac_max}
