@@ -44,7 +44,7 @@ class PsfMeta(ctypes.Structure):
         ("prog_chunks", ctypes.c_int32),
         ("prog_steps", ctypes.c_int32),
         ("flags", ctypes.c_int32),
-        ("prog_segs", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("prog_segs", ctypes.c_int32), ("prog_group_w", ctypes.c_int16), ("prog_shear", ctypes.c_int16),
         ("sy", ctypes.c_double), ("sx", ctypes.c_double),
         ("syy", ctypes.c_double), ("sxx", ctypes.c_double), ("sxy", ctypes.c_double),
     ]

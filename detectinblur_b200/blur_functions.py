@@ -108,8 +108,7 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     exact = _exact_default() if exact is None else exact
     if n == 0:
         return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
-    if images[0].dtype == torch.float16 and not exact and not _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd,
-                                                                             clamp, philox_seed, gamma, pad_mode):
+    if images[0].dtype == torch.float16 and not exact:
         return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode)
     dev = images[0].device
     dtype = images[0].dtype

@@ -13,13 +13,9 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
 
 static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
     if (meta_host == nullptr || im.psf_index < 0) return false;
-    if (io_dtype == DIB_F16) {
-        // half I/O: fp32 accumulation, rounded to half once (the reference's half loop rounds after every tap -- callers
-        // that need its bits pass DIB_ALGO_GENERIC).  Needs 16-byte-aligned destination rows and at most the normalize epilogue.
-        if ((reinterpret_cast<uintptr_t>(im.dst) & 15u) || (im.dst_row_pitch & 7) || (im.dst_chan_pitch & 7)) return false;
-        if (reinterpret_cast<uintptr_t>(im.src) & 1u) return false;
-        if (im.epilogue & ~DIB_EPI_NORMALIZE) return false;
-    }
+    // float32 images only: half images go through the wrapper's casts (fp32 accumulation, one rounding) or, for the
+    // reference's bits, the exact-order kernel
+    if (io_dtype != DIB_F32) return false;
     // reflect-101 or zero padding about centre 63; tiny images (the reference's own zero-padding case) stay on the generic kernel
     if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return false;
     const dib_psf_meta& m = meta_host[im.psf_index];

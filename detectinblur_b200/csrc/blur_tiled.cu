@@ -1,110 +1,81 @@
-// Tiled sparse-PSF blur for sm_100a (DIB_ALGO_TILED): the fast path of dib_blur_batch (float and half I/O).
+// Tiled sparse-PSF blur for sm_100a (DIB_ALGO_TILED): the fast path of dib_blur_batch.
 //
 // Replaces the per-tap `output += torch.roll(pad(image), shift) * w` loop of manual_blur
 // (models/blur_functions.py:59-69) -- O(taps) launches and ~7 passes over the padded tensor per tap -- with one
 // persistent, warp-specialised launch per batch:
-//   * work unit  = one 36 x 448 output tile of one channel of one image; the CTAs (one per SM) take tiles from a
-//                  global ticket counter, images with the heaviest PSFs first;
-//   * producers  = one warpgroup (4 warps, 56 registers after setmaxnreg.dec).  For every stage (tile x program chunk)
-//                  thread t stages row t of tile + halo global -> shared: one TMA bulk copy (cp.async.bulk) for the
-//                  16-byte-aligned interior of the row segment, 4-byte cp.async for the <= 3 unaligned floats at each
-//                  row end and, shared out over all producer threads, for the reflect-101 border columns, all completing
-//                  on the stage's "full" mbarrier.  Rows are independent copies, so reflected rows cost nothing extra
-//                  and the reference's native unpitched CHW layout (row pitch 5332 B for W = 1333) needs no repacking;
-//                  a row table records each row's 0-3 float skew.  Two stages are in flight; a refill waits on the
-//                  stage's "empty" mbarrier.  Half-precision images: the rows land as halves in the second half of
-//                  their own bytes and the producer warps widen them in place (issue_stage_half);
-//   * consumers  = twelve warps (6 x 2 over the tile, three per SM sub-partition, 152 registers after
-//                  setmaxnreg.inc).  Each thread owns a 6-row x 7-column output block (lanes sit 7 floats apart in a
-//                  row: odd stride -> conflict-free scalar LDS); rows r and r + 3 share 64-bit accumulators and every
-//                  multiply-add is a packed FFMA2.  Taps are consumed as the program built by taps.cu: groups of 4 PSF
-//                  columns swept row by row; a rotating 6 x 10 register window of the input slides with the sweep
-//                  (one new row per step, loaded into the slot the previous step freed, consumed last).  Absent taps
-//                  inside a group are skipped with warp-uniform branches (21 FFMA2 each);
+//   * work unit  = one kTH x kTW (32 x 448) output tile of one channel of one image; the CTAs (one per SM) take tiles
+//                  from a global ticket counter, images with the heaviest PSFs first;
+//   * producers  = one warpgroup (4 warps, 56 registers after setmaxnreg.dec).  Every image carries a ONE-DIMENSIONAL TMA
+//                  tensor map over its elements (kernel parameter), so a staged row is two `cp.async.bulk.tensor.1d` boxes
+//                  of 256 floats (SASS UTMALDG) whatever the row pitch: the reference's unpitched CHW layout (5332 B per
+//                  row for W = 1333) needs no repacking and no per-row head / tail handling.  A box must start 16-byte
+//                  aligned in global memory (measured: tools/exp/tma1d_probe.cu), so a row's box starts at the aligned
+//                  element at or below its first wanted pixel and the row sits `skew` = 0..3 floats into its
+//                  shared-memory row; for consecutive image rows the skew is an arithmetic progression mod 4 (step =
+//                  row pitch mod 4), which the consumers fold into four precomputed addresses.  What a linear box cannot
+//                  give -- rows above / below the image (reflect-101 or zeros) and the columns left and right of it --
+//                  is patched by the producer threads once the boxes have landed (4-byte cp.async from the mirrored
+//                  pixel, placed where the arithmetic progression expects it), then the stage is handed to the
+//                  consumers through the "full" mbarrier.  Two stages are in flight;
+//   * consumers  = kComputeWarps warps (4 x 2 over the tile, two per SM sub-partition, 224 registers after
+//                  setmaxnreg.inc).  Each thread owns an 8-row x 7-column output block (lanes sit 7 floats apart in a
+//                  row: odd stride -> conflict-free scalar LDS); rows r and r + 4 share 64-bit accumulators and every
+//                  multiply-add is a packed FFMA2.  Taps are consumed as the program built by taps.cu: the PSF support,
+//                  sheared so that a slanted streak becomes near-vertical, is cut into groups of 2 (or 4) columns; a group
+//                  is swept row by row with a rotating 8-row register window of the input (one new row per step, loaded
+//                  into the slot the previous step freed, consumed last) and EVERY step executes all taps of the group
+//                  -- zero weights where the PSF has none -- so the sweep has no data-dependent branch at all.  The
+//                  output block of a thread is sheared like the program (row r is shifted by shear * r columns), which
+//                  makes the window's column offset a constant per step;
 //   * epilogue   = noise / clamp / gamma / (x - mean) / std (blur_functions.py:72-74, net_transforms.py:135-139) fused
 //                  on the way out, per warp and without block-level barriers: accumulators -> the warp's private
-//                  two-row buffer -> 16-byte vector stores.  Destinations with 16-byte-aligned rows take a lean store;
-//                  others stage each row skewed to its global address phase and store the <= 3 unaligned floats at
-//                  each row end one by one.
+//                  two-row buffer -> 16-byte vector stores.
 // No tensor cores: the contraction is sparse and data dependent.  Results differ from the exact-order kernel only
 // by FMA contraction and tap order (measured <= 4e-7 on [0,1] images; bound 1e-5).
+#include <cuda.h>
+
 #include "dib_common.cuh"
 
 namespace dib {
 
-// Shape of the register tiling.  Every thread owns a 2*kR-row x kCC-column output block and treats rows r and r + kR
-// as a PAIR: their accumulators share a 64-bit register and every multiply-add is a packed FFMA2 (fma.rn.f32x2: one
-// issue slot, two FMAs -- measured 62 TFLOP/s at 8 warps/SM where 3-register FFMA reaches 50), which leaves issue
-// slots for the window loads and the sweep control.  The pair's input rows are the same sliding window kR steps
-// apart, so one new row per step feeds both halves.  The unrolled sweep body is 2*kR (rotations) x kGroupW (tap
-// columns) x kR * kCC FFMA2 of 16 bytes = 8 KB: it has to stay in the instruction cache (a 29 KB body stalled on
-// instruction fetch as often as it issued, profiles/round1_notes.md).  kR = 3 keeps a compute thread at ~130
-// registers, so 12 compute warps (three per SM sub-partition) fit beside the producer warpgroup; kR = 4 needs 172
-// registers, allows only 8 compute warps and measured 5 % slower; kR = 2 with 16 compute warps (104 registers) has
-// more warps to hide latency with but a third fewer FMAs per window load and measured 7 % slower.  (Its first build
-// hung: setmaxnreg.inc asked for more registers than the CTA's launch-time allocation holds -- see kLaunchRegs.)
-#ifndef DIB_R
-#define DIB_R 3
-#endif
-#ifndef DIB_WARP_ROWS
-#define DIB_WARP_ROWS 6
-#endif
-#ifndef DIB_WARP_COLS
-#define DIB_WARP_COLS 2
-#endif
 #ifndef DIB_PRODUCER_REGS
-#define DIB_PRODUCER_REGS 56      // 12 x 32 x 152 + 4 x 32 x 56 = 65536: the compute warps cannot use the difference to 40 anyway
+#define DIB_PRODUCER_REGS 56
 #endif
-constexpr int kR = DIB_R;                   // row pairs per thread
-constexpr int kRows = 2 * kR;               // output rows per thread (= rotation period of the register window)
-constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
-constexpr int kWarpW = 32 * kCC;            // 224 output columns per warp
-constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps are arranged kWarpRows x kWarpCols over the tile
-constexpr int kWarpCols = DIB_WARP_COLS;
-constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: equal load on the 4 SM sub-partitions
-constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
+constexpr int kProducerWarps = 4;           // one warpgroup: a thread issues at most one TMA box per stage
+constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
 constexpr int kProducerRegs = DIB_PRODUCER_REGS;   // setmaxnreg budgets; together they must fit the 64K-register file
 // setmaxnreg moves registers inside the CTA's launch-time allocation (threads x the per-thread count the launch bound
 // allows, a multiple of 8); asking for more than the producers hand back blocks forever.
 constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8 > 255 ? 248 : (65536 / kThreads) / 8 * 8;
-constexpr int kComputeRegsRaw = (kThreads * kLaunchRegs - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32) / 8 * 8;
+constexpr int kComputeRegsRaw = (kThreads * kLaunchRegs - kProducerThreads * kProducerRegs) / (kComputeWarps * 32) / 8 * 8;
 constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
 static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
-constexpr int kTH = kWarpRows * kRows;      // 36 output rows per tile
-constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
-constexpr int kWinW = kCC + kGroupW - 1;    // 10 input columns feed one group
-constexpr int kRowsMax = kTH + kChunkHaloRows;                     // 56 staged rows
-// Staged row: tile + halo + the row's skew (<= 3 floats for fp32 rows, <= 7 for half rows), rounded to 8 floats so that the
-// second half of a row's bytes -- where half-precision rows land before they are widened in place -- is 16-byte aligned.
-constexpr int kPitch = ((kTW + kChunkGroups * kGroupW - 1 + 7) + 7) / 8 * 8;   // 480 floats
-constexpr int kOutPitch = kWarpW + 4;       // one staged output row of a warp (skew <= 3)
-constexpr int kHdrBytes = 64;
-constexpr int kAuxBytes = (kChunkDataMax + 15) / 16 * 16;          // segment records + weights of one chunk
-constexpr int kRowTabBytes = ((kRowsMax * 4) + 15) / 16 * 16;
-constexpr int kTileBytes = kRowsMax * kPitch * 4;
-constexpr int kStageBytes = kHdrBytes + kAuxBytes + kRowTabBytes + kTileBytes;
-constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;    // two staged rows per compute warp
-constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 64;    // + 4 mbarriers + 2 tile-ticket slots
-static_assert(kRowsMax <= kProducerWarps * 32, "one staged row per producer thread");
-static_assert(kPitch % 8 == 0 && kPitch >= kTW + kChunkGroups * kGroupW - 1 + 7, "pitch must hold tile + halo + skew");
-static_assert(kStageBytes % 16 == 0, "stage must keep 16-byte alignment");
+constexpr int kBoxElems = 256;              // elements per TMA box (the hardware maximum per dimension)
+constexpr int kBoxesPerRow = kPitch / kBoxElems;
+constexpr int kRowBytes = kPitch * 4;
+constexpr int kTileBytes = kRowsMax * kRowBytes;
+constexpr int kStageBytes = kStageHdrBytes + kChunkAuxBytes + kTileBytes;
+constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 128;    // + 6 mbarriers + 2 tile-ticket slots
+static_assert(kRowsMax * kBoxesPerRow <= kProducerThreads, "one TMA box per producer thread");
+static_assert((kStageHdrBytes + kChunkAuxBytes) % 128 == 0 && kStageBytes % 128 == 0, "TMA destinations are 128-byte aligned");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
-struct TiledImage {
-    const void* src;      // float or __half (kernel template), pitches in elements
+struct alignas(64) TiledImage {
+    CUtensorMap tmap;     // 1-D map over the image's elements, from the 16-byte-aligned address at or below src
+    const void* src;      // float, pitches in elements
     void* dst;
     const float* noise;
     int64_t src_rp, src_cp, dst_rp, dst_cp;
+    int src_off;          // elements between the tensor map's base and src
     int C, H, W;
     int tiles_x, tiles_y;
     int first_tile;       // tiles of the images before this one
     int psf_index, nchunks;
+    int shear;            // the program's shear: output row r of a warp's block starts shear * r columns further right
     int epilogue;
     int zero_pad;         // DIB_PAD_ZERO128: pixels outside the image read as 0 instead of being mirrored
     int aligned_out;      // every destination row starts 16-byte aligned (base, row pitch and channel pitch): lean row store
-    int rec0_valid;       // single-chunk PSF: its one chunk record, rebuilt on the host from the PSF summary, rides in the
-    ChunkRec rec0;        // kernel parameters, so a tile's first stage need not wait for a load from the program section
     int philox_slot;      // position in the caller's batch (Philox stream id)
     float noise_sd, gamma;
     float mean[4], std[4];
@@ -137,24 +108,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-#ifdef DIB_NO_HINT
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-#endif
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware, do not spin
 }
-// TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// TMA: one box of a 1-D tensor map, global -> shared, completion counted in bytes on the mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_box_1d(uint32_t dst, const CUtensorMap* map, int coord, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(coord), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+// TMA bulk copy global -> shared of a 16-byte-aligned span (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 // arrive on the mbarrier once all cp.async issued so far by this thread have landed (counts as a normal arrival)
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
@@ -168,36 +152,28 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int lds_s32(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void lds_entry(uint32_t addr, float& w, int& code) {
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(w), "=r"(code) : "r"(addr));
+__device__ __forceinline__ void lds_entry(uint32_t addr, int& a, int& b) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
 }
 __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
-__device__ __forceinline__ uint2 lds_v2u(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+__device__ __forceinline__ float2 lds_v2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
-// four halves (8 bytes) -> four floats at addr .. addr + 15
-__device__ __forceinline__ void sts_widened(uint32_t addr, const uint2& h4) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h4.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h4.y));
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "f"(0.0f) : "memory");
 }
 
 __device__ __forceinline__ int reflect101(int v, int n) {
     v = v < 0 ? -v : v;
     v = v >= n ? 2 * (n - 1) - v : v;
-    return min(max(v, 0), n - 1);     // clamp only guards rows/cols that feed masked outputs
+    return min(max(v, 0), n - 1);     // clamp only guards rows/cols that feed zero weights or masked outputs
 }
 
 // ---------------------------------------------------------------- stage bookkeeping
@@ -206,9 +182,10 @@ struct __align__(16) StageHdr {
     int tile;           // global tile index; -1 = no more work
     int img, ch, i0, j0;
     int first_chunk, last_chunk;
-    int dy_hi, dx_hi, nseg, wsteps;
+    int dy_hi, dx_hi, nseg, group_w, shear;
+    int skew0, dskew;   // staged row r holds image column cl at float offset (skew0 + r * dskew) & 3
 };
-static_assert(sizeof(StageHdr) <= kHdrBytes, "stage header too large");
+static_assert(sizeof(StageHdr) <= kStageHdrBytes, "stage header too large");
 
 struct Stage {
     int tile;       // global tile index, -1: none
@@ -217,22 +194,7 @@ struct Stage {
     ChunkRec rec;
 };
 
-struct StageSmem {
-    StageHdr* hdr;
-    uint8_t* aux;       // SegRec slots + weight vectors of the chunk
-    int* rowtab;        // float offset of image column `cl` inside each staged row
-    float* tile;
-};
-
-__device__ __forceinline__ StageSmem stage_smem(uint8_t* base, int b) {
-    StageSmem s;
-    uint8_t* p = base + (size_t)b * kStageBytes;
-    s.hdr = reinterpret_cast<StageHdr*>(p);
-    s.aux = p + kHdrBytes;
-    s.rowtab = reinterpret_cast<int*>(p + kHdrBytes + kAuxBytes);
-    s.tile = reinterpret_cast<float*>(p + kHdrBytes + kAuxBytes + kRowTabBytes);
-    return s;
-}
+__device__ __forceinline__ uint32_t stage_base(uint32_t smem_base, int b) { return smem_base + (uint32_t)b * kStageBytes; }
 
 __device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stage& st) {
     int n = 0;
@@ -249,7 +211,6 @@ __device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stag
 }
 
 __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img, int chunk) {
-    if (p.img[img].rec0_valid) return p.img[img].rec0;          // single-chunk PSF (chunk == 0)
     const uint8_t* prog = p.prog + (size_t)p.img[img].psf_index * kProgBytes;
     const int4 v = __ldg(reinterpret_cast<const int4*>(prog) + chunk);
     ChunkRec r;
@@ -257,9 +218,12 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
     r.dy_hi = (int16_t)(v.x >> 16);
     r.dx_lo = (int16_t)(v.y & 0xffff);
     r.dx_hi = (int16_t)(v.y >> 16);
-    r.nseg = (int16_t)(v.z & 0xffff);
-    r.wsteps = (int16_t)(v.z >> 16);
-    r.data_off = v.w;
+    r.wsteps = (int16_t)(v.z & 0xffff);
+    r.nseg = (uint8_t)((v.z >> 16) & 0xff);
+    r.shear = (int8_t)((v.z >> 24) & 0xff);
+    r.group_w = (uint8_t)(v.w & 0xff);
+    r.pad = 0;
+    r.data_off16 = (uint16_t)((unsigned)v.w >> 16);
     return r;
 }
 
@@ -273,7 +237,7 @@ __device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int&
         const unsigned t = nfetch == 0 ? blockIdx.x : gridDim.x + atomicAdd(&p.sched->next_tile, 1u);
         *slot = t < (unsigned)p.total_tiles ? (int)t : -1;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
     ++nfetch;
     return *slot;
 }
@@ -296,216 +260,102 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
 }
 
-// Producer group (4 warps): issue every load of one stage.  Thread t owns staged row t: it places the row (skewed so
-// that the 16-byte-aligned interior of the in-image segment lands 16-byte aligned), moves that interior with one TMA
-// bulk copy and fetches the <= 3 + 3 unaligned end floats with 4-byte cp.async.  Tiles that reach past the left /
-// right image border then get their reflect-101 columns, each warp covering the rows its own lanes placed.  In
-// zero-padding mode rows and columns outside the image are stored as zeros instead (plain shared-memory stores, which
-// the thread's own arrive on the stage barrier publishes to the consumers).
-__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* bar, int pt,
-                                            uint64_t* empty_bar, uint32_t empty_parity, bool wait_empty) {
+// geometry of a stage: image row of staged row 0, staged rows, image column of staged column 0, last staged image column
+struct StageGeom {
+    int rt, nrows, cl, cr;
+    int skew0, dskew;       // image column cl sits (skew0 + r * dskew) & 3 floats into staged row r
+};
+__device__ __forceinline__ StageGeom stage_geom(const TiledImage& im, const Stage& st) {
+    StageGeom g;
+    const int shear = st.rec.shear;
+    const int pad = (kRows - 1) * (shear < 0 ? -shear : shear);   // a warp's sheared block reaches this far left of its nominal origin
+    g.rt = st.i0 - st.rec.dy_hi;
+    g.nrows = kTH + st.rec.dy_hi - st.rec.dy_lo;
+    g.cl = st.j0 - pad - st.rec.dx_hi;
+    g.cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;
+    // element index (from the tensor map's aligned base) of (row rt, column cl), as if the image continued above row 0
+    const int64_t e0 = (int64_t)im.src_off + (int64_t)st.ch * im.src_cp + (int64_t)g.rt * im.src_rp + g.cl;
+    g.skew0 = (int)(e0 & 3);
+    g.dskew = (int)(im.src_rp & 3);
+    return g;
+}
+
+// Producer group, first half of a stage: start every bulk load.  Thread t issues box (t mod 2) of staged row t / 2: 256
+// consecutive elements of the image row from the 16-byte-aligned element at or below image column cl (+ 256) -- elements
+// before the row's first or past its last pixel are neighbouring rows' pixels (or zeros outside the tensor) and are
+// patched by finish_stage, like the rows above and below the image, which no box is issued for.
+__device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& st, uint32_t sbase, uint64_t* landed, int pt) {
     const TiledImage& im = p.img[st.img];
-    const int lane = pt & 31, pw = pt >> 5;
-    const int sr = lane * kProducerWarps + pw;                             // rows interleave over the producer warps
-    const int rt = st.i0 - st.rec.dy_hi;                                  // image row of staged row 0
-    const int nrows = kTH + st.rec.dy_hi - st.rec.dy_lo;
-    const int cl = st.j0 - st.rec.dx_hi;                                  // image column of staged column 0
-    const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;            // last staged image column
-    const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;              // in-image part [xa, xb1)
-    const float* plane = static_cast<const float*>(im.src) + (int64_t)st.ch * im.src_cp;
-    // Where this thread's row comes from and where it goes: pure arithmetic, done before the wait for the buffer so that
-    // the copies go out as soon as the consumers release it.
-    const float* gp = plane;
-    int ro = sr * kPitch;
-    int xa_al = cl, xb_al = cl;              // nothing inside the image: every column is mirrored
-    const bool in_rows = sr < nrows;
-    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
-    if (in_rows && !zero_row) {
-        gp = plane + (int64_t)reflect101(rt + sr, im.H) * im.src_rp;
-        if (xb1 > xa) {
-            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 2);
-            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 3u);
-            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 3u);
-            if (xb_al <= xa_al) xa_al = xb_al = xa;      // segment shorter than one aligned quad
-        }
-        ro += (int)((uint32_t)(cl - xa_al) & 3u);       // skew: makes (xa_al - cl + skew) a multiple of 4
-    }
-    float* drow = sm.tile + ro - cl;                     // drow[col] addresses image column col
-    const uint32_t nb_row = (in_rows && !zero_row) ? (uint32_t)(xb_al - xa_al) * 4u : 0u;
-    if (wait_empty) mbar_wait(empty_bar, empty_parity);  // consumers released the stage that used this buffer
+    const StageGeom g = stage_geom(im, st);
     fence_proxy_async();   // order the consumers' generic-proxy reads of this buffer before the async-proxy writes
     if (pt == 0) {
         StageHdr h;
         h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
         h.first_chunk = (st.chunk == 0);
         h.last_chunk = (st.chunk + 1 == im.nchunks);
-        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
-        *sm.hdr = h;
+        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.group_w = st.rec.group_w; h.shear = st.rec.shear;
+        h.skew0 = g.skew0; h.dskew = g.dskew;
+        StageHdr* hp = reinterpret_cast<StageHdr*>(__cvta_shared_to_generic(sbase));
+        *hp = h;
     }
-    uint32_t bytes = nb_row;
-    if (in_rows && zero_row) {
-        for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
-    } else if (in_rows) {
-        if (nb_row) tma_bulk_g2s(drow + xa_al, gp + xa_al, nb_row, bar);
-        for (int col = xa; col < xa_al; ++col) cp_async_4(drow + col, gp + col);      // unaligned head
-        for (int col = xb_al; col < xb1; ++col) cp_async_4(drow + col, gp + col);     // unaligned tail
+    const uint32_t aux = sbase + kStageHdrBytes, tile = aux + kChunkAuxBytes;
+    const uint32_t aux_bytes = (uint32_t)(kChunkSegBytes + 4 * st.rec.group_w * (st.rec.wsteps + 1) + 15) & ~15u;
+    const int row = pt / kBoxesPerRow, box = pt - row * kBoxesPerRow;
+    const int irow = g.rt + row;
+    if (row < g.nrows && irow >= 0 && irow < im.H) {
+        const int64_t e = (int64_t)im.src_off + (int64_t)st.ch * im.src_cp + (int64_t)irow * im.src_rp + g.cl;
+        tma_box_1d(tile + (uint32_t)row * kRowBytes + (uint32_t)box * (kBoxElems * 4), &im.tmap, (int)(e & ~int64_t(3)) + box * kBoxElems, landed);
     }
-    if (sr < kRowsMax) sm.rowtab[sr] = ro;   // rows past a partial tile are read (results discarded): offsets stay in range
-    if (pt == 32) {
-        const uint32_t nb = (uint32_t)(kChunkSegBytes + kStepBytes * (st.rec.wsteps + 1));
-        tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, bar);
-        bytes += nb;
+    if (pt == kProducerThreads - 1)
+        tma_bulk_g2s(aux, p.prog + (size_t)im.psf_index * kProgBytes + (size_t)st.rec.data_off16 * 16, aux_bytes, landed);
+    if (pt == 0) {
+        const int rows_in = max(0, min(g.rt + g.nrows, im.H) - max(g.rt, 0));
+        mbar_arrive_expect_tx(landed, (uint32_t)rows_in * kRowBytes + aux_bytes);
     }
-    if (cl < 0 || cr >= im.W) {
-        // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels (4-byte cp.async each), or zeros in
-        // zero-padding mode.  All producer threads share the (row, column) pairs; the row table tells where a row sits.
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
-        const int total = nrows * ncols;
-        for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
-            const int r2 = idx / ncols, k = idx - r2 * ncols;
-            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
-            const int irow = rt + r2;
-            float* d = sm.tile + sm.rowtab[r2] - cl + col;
-            if (im.zero_pad) {
-                if (irow >= 0 && irow < im.H) *d = 0.0f;           // rows outside the image are already all zeros
-            } else {
-                cp_async_4(d, plane + (int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W));
-            }
-        }
-    }
-    mbar_arrive_expect_tx(bar, bytes);
-    cp_async_mbar_arrive(bar);
 }
 
-// Half-precision I/O: the same stage built from __half rows.  Thread t places row t's 16-byte-aligned interior, as
-// halves, in the SECOND half of the row's bytes with one TMA bulk copy (skewed so that global and shared addresses
-// agree mod 16 bytes); when the stage's copies have landed (`landed` barrier) the producer warps widen the rows in place,
-// front to back -- the float written for element p ends at byte 4p + 4, never past a half still to be read at byte
-// 2 * kPitch + 2p' of a later group -- and then fill in what TMA cannot move: the <= 7 + 7 unaligned end elements and the mirrored (or zero) border columns,
-// read straight from global memory.  The consumers see exactly the fp32 tile of the float path.
-__device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Stage& st, const StageSmem& sm, uint64_t* landed,
-                                                 uint32_t landed_parity, uint64_t* full, int pt) {
+// Producer group, second half of a stage: once the boxes have landed, write what they could not deliver -- every pixel of
+// the staged rows above / below the image and, in the other rows, the columns left of the image's first and right of its
+// last pixel: reflect-101 pixels (4-byte cp.async from the mirrored source) or zeros -- each at the float offset the skew
+// progression assigns to its row, and hand the stage to the consumers: every producer thread arrives on "full" when its
+// own patches have landed.
+__device__ __forceinline__ void finish_stage(const TiledParams& p, const Stage& st, uint32_t sbase, uint64_t* landed, uint32_t parity,
+                                             uint64_t* full, int pt) {
     const TiledImage& im = p.img[st.img];
-    const int lane = pt & 31, pw = pt >> 5;
-    const int sr = lane * kProducerWarps + pw;
-    const int rt = st.i0 - st.rec.dy_hi;
-    const int nrows = kTH + st.rec.dy_hi - st.rec.dy_lo;
-    const int cl = st.j0 - st.rec.dx_hi;
-    const int cr = min(st.j0 + kTW, im.W) - 1 - st.rec.dx_lo;
-    const int xa = max(cl, 0), xb1 = min(cr, im.W - 1) + 1;
-    const __half* plane = static_cast<const __half*>(im.src) + (int64_t)st.ch * im.src_cp;
-    fence_proxy_async();
-    if (pt == 0) {
-        StageHdr h;
-        h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
-        h.first_chunk = (st.chunk == 0);
-        h.last_chunk = (st.chunk + 1 == im.nchunks);
-        h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
-        *sm.hdr = h;
-    }
-    uint32_t bytes = 0;
-    const __half* gp = plane;
-    int ro = sr * kPitch;
-    int xa_al = cl, xb_al = cl;
-    const bool in_rows = sr < nrows;
-    const bool zero_row = im.zero_pad && (rt + sr < 0 || rt + sr >= im.H);
-    if (in_rows && !zero_row) {
-        gp = plane + (int64_t)reflect101(rt + sr, im.H) * im.src_rp;
-        if (xb1 > xa) {
-            const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 1);       // in halves
-            xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 7u);
-            xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 7u);
-            if (xb_al <= xa_al) xa_al = xb_al = xa;
-        }
-        ro += (int)((uint32_t)(cl - xa_al) & 7u);       // skew: (xa_al - cl + skew) is a multiple of 8
-        const uint32_t nb = (uint32_t)(xb_al - xa_al) * 2u;
-        if (nb) {
-            __half* hrow = reinterpret_cast<__half*>(sm.tile + sr * kPitch) + kPitch;      // the row's second half
-            tma_bulk_g2s(hrow + (ro - sr * kPitch) + (xa_al - cl), gp + xa_al, nb, landed);
-            bytes += nb;
-        }
-    }
-    if (sr < kRowsMax) sm.rowtab[sr] = ro;
-    if (pt == 32) {
-        const uint32_t nb = (uint32_t)(kChunkSegBytes + kStepBytes * (st.rec.wsteps + 1));
-        tma_bulk_g2s(sm.aux, p.prog + (size_t)im.psf_index * kProgBytes + st.rec.data_off, nb, landed);
-        bytes += nb;
-    }
-    mbar_arrive_expect_tx(landed, bytes);
-    // the <= 7 + 7 unaligned end elements of the row: independent global loads, in flight while the bulk copies land
-    __half head[7], tail[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        head[j] = (in_rows && !zero_row && xa + j < xa_al) ? gp[xa + j] : __half(0.0f);
-        tail[j] = (in_rows && !zero_row && xb_al + j < xb1) ? gp[xb_al + j] : __half(0.0f);
-    }
-    mbar_wait(landed, landed_parity);
-    float* drow = sm.tile + ro - cl;                  // drow[col] addresses image column col
-    // Widen the aligned interiors in place.  A warp takes the rows its own lanes placed, one row at a time, a lane per
-    // group of 8 elements: every lane first reads its 16 bytes of halves, then -- after a warp barrier -- writes its 32
-    // bytes of floats.  Within a round of 32 groups the floats land on halves that the round has already read (a float
-    // group ends at byte 32 g + 32, the half group it may reach starts at 2 * kPitch + 16 g); rounds ascend along the row.
-    {
-        static_assert(kPitch / 4 <= 128, "four chunks per lane cover a staged row");
-        static_assert(kRowsMax * kPitch < (1 << 20), "row offset and group count share one shuffled word");
-        const int my_n8 = (in_rows && !zero_row) ? (xb_al - xa_al) >> 3 : 0;
-        const int packed = (ro - cl + xa_al) | (my_n8 << 20);             // float index of the first aligned element | groups
-        // A lane widens four 4-element chunks per row, 32 chunks apart: every load (8 bytes per lane) and every store (16
-        // bytes per lane) of the warp covers one contiguous span, so neither has bank conflicts.
-        const uint32_t tile_b = smem_u32(sm.tile);
-        uint32_t hb = tile_b + 2u * kPitch * (uint32_t)(pw + 1) + 8u * (uint32_t)lane;      // row pw's halves; + 2 * off
-        const uint32_t fb = tile_b + 16u * (uint32_t)lane;                                    // + 4 * off
-        const int nl = (nrows - pw + kProducerWarps - 1) / kProducerWarps;                   // rows this warp placed
-        for (int l = 0; l < nl; ++l, hb += 2u * kPitch * kProducerWarps) {
-            const int pk = __shfl_sync(0xffffffffu, packed, l);
-            const uint32_t off = (uint32_t)(pk & 0xfffff);
-            const int n4 = (pk >> 20) * 2;                                  // 4-element chunks of the row (<= 120)
-            const uint32_t h0 = hb + 2u * off, f0 = fb + 4u * off;
-            uint2 hv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                hv[j] = make_uint2(0u, 0u);
-                if (lane + 32 * j < n4) hv[j] = lds_v2u(h0 + 256u * j);
+    const StageGeom g = stage_geom(im, st);
+    mbar_wait(landed, parity);
+    const int top = min(g.nrows, max(0, -g.rt));                              // staged rows above the image
+    const int bot = min(g.nrows - top, max(0, g.rt + g.nrows - im.H));         // staged rows below it
+    if (top > 0 || bot > 0 || g.cl < 0 || g.cr >= im.W) {
+        const uint32_t tile = sbase + kStageHdrBytes + kChunkAuxBytes;
+        const float* plane = static_cast<const float*>(im.src) + (int64_t)st.ch * im.src_cp;
+        const int ncols = g.cr - g.cl + 1;
+        const int xa = max(g.cl, 0), xb1 = min(g.cr, im.W - 1) + 1;          // in-image columns [xa, xb1)
+        const int nleft = xa - g.cl, nborder = nleft + g.cr + 1 - xb1;
+        const int n_out = (top + bot) * ncols;
+        const int total = n_out + (g.nrows - top - bot) * nborder;
+        for (int idx = pt; idx < total; idx += kProducerThreads) {
+            int r2, col;
+            if (idx < n_out) {                       // a row outside the image: all of its columns
+                const int q = idx / ncols;
+                r2 = q < top ? q : g.nrows - bot + (q - top);
+                col = g.cl + (idx - q * ncols);
+            } else {                                 // a row inside the image: its border columns
+                const int k2 = idx - n_out, q = k2 / nborder, k = k2 - q * nborder;
+                r2 = top + q;
+                col = k < nleft ? g.cl + k : xb1 + (k - nleft);
             }
-            __syncwarp();                                                  // the whole row is read before any of it is written
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (lane + 32 * j < n4) sts_widened(f0 + 512u * j, hv[j]);
-        }
-        __syncwarp();
-    }
-    if (in_rows && zero_row) {
-        for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
-    } else if (in_rows) {
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            if (xa + j < xa_al) drow[xa + j] = __half2float(head[j]);
-            if (xb_al + j < xb1) drow[xb_al + j] = __half2float(tail[j]);
+            const int irow = g.rt + r2;
+            const int skew = (g.skew0 + r2 * g.dskew) & 3;
+            const uint32_t d = tile + (uint32_t)r2 * kRowBytes + 4u * (uint32_t)(col - g.cl + skew);
+            if (im.zero_pad)
+                sts_f32(d, 0.0f);
+            else
+                cp_async_4(d, plane + (int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W));
         }
     }
-    if (cl < 0 || cr >= im.W) {
-        // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels, or zeros in zero-padding mode.  All
-        // producer threads share the (row, column) pairs; the row table written above tells where each row sits.
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
-        const int total = nrows * ncols;
-#pragma unroll 4
-        for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
-            const int r2 = idx / ncols, k = idx - r2 * ncols;
-            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
-            const int irow = rt + r2;
-            float v = 0.0f;
-            bool write = true;
-            if (im.zero_pad) {
-                write = irow >= 0 && irow < im.H;            // rows outside the image are already all zeros
-            } else {
-                v = __half2float(plane[(int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W)]);
-            }
-            if (write) sm.tile[sm.rowtab[r2] - cl + col] = v;
-        }
-    }
-    mbar_arrive(full);          // release: this thread's shared-memory writes are visible to whoever observes the phase
+    __threadfence_block();      // zero fills are plain stores: order them before the arrive that publishes the stage
+    cp_async_mbar_arrive(full);
 }
 
 // ---------------------------------------------------------------- compute
@@ -524,8 +374,8 @@ __device__ __forceinline__ float2 ffma2(float w, float2 x, float2 a) {
 // The window holds the kRows input rows of the current step.  Logical row q sits in slot (q - U) mod kRows at
 // rotation U; slot j < kR is win[j].x, slot j + kR is win[j].y, so the two rows of a pair (q and q + kR) always share
 // one 64-bit register -- in swapped halves for half of the rotations, which FFMA2's operand swizzle absorbs.
-template <int U, int Q>
-__device__ __forceinline__ float2 window_pair(const float2 (&win)[kR][kWinW], int k) {
+template <int W, int U, int Q>
+__device__ __forceinline__ float2 window_pair(const float2 (&win)[kR][W], int k) {
     constexpr int slot = ((Q - U) % kRows + kRows) % kRows;
     if constexpr (slot < kR)
         return win[slot][k];
@@ -533,32 +383,34 @@ __device__ __forceinline__ float2 window_pair(const float2 (&win)[kR][kWinW], in
         return make_float2(win[slot - kR][k].y, win[slot - kR][k].x);
 }
 
-// One tap of a sweep step: weight w multiplies the window shifted by E columns.  Pair 0 contains the row loaded at
-// the start of this step and is consumed last, so the FMAs on the older rows cover that load's latency.
-template <int U, int E>
-__device__ __forceinline__ void fma_tap(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kWinW], const float w) {
+// All taps of one step on row pair P: weight w[e] multiplies the window shifted by e columns.
+template <int G, int U, int P>
+__device__ __forceinline__ void fma_pair(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kCC + G - 1], const float (&w)[G]) {
 #pragma unroll
-    for (int rr = 1; rr <= kR; ++rr) {
-        const int r = rr % kR;
+    for (int e = 0; e < G; ++e) {
 #pragma unroll
-        for (int c = 0; c < kCC; ++c) {
-            float2 x;
-            // constexpr dispatch on the pair index (r is a compile-time constant after unrolling)
-            if (r == 0) x = window_pair<U, 0>(win, c - E + kGroupW - 1);
-            else if (r == 1) x = window_pair<U, 1>(win, c - E + kGroupW - 1);
-            else if (r == 2) x = window_pair<U, 2>(win, c - E + kGroupW - 1);
-            else x = window_pair<U, 3>(win, c - E + kGroupW - 1);
-            acc[r][c] = ffma2(w, x, acc[r][c]);
-        }
+        for (int c = 0; c < kCC; ++c) acc[P][c] = ffma2(w[e], window_pair<kCC + G - 1, U, P>(win, c - e + G - 1), acc[P][c]);
     }
 }
-static_assert(kR <= 4, "fma_tap dispatches on at most 4 row pairs");
+template <int G, int U, int P>
+struct PairLoop {      // pairs kR-1 .. 1, then pair 0: it contains the row loaded at the start of the step and goes last
+    __device__ __forceinline__ static void run(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kCC + G - 1], const float (&w)[G]) {
+        fma_pair<G, U, P>(acc, win, w);
+        if constexpr (P > 0) PairLoop<G, U, (P == 1 ? 0 : P - 1)>::run(acc, win, w);
+    }
+};
+template <int G, int U>
+struct PairLoop<G, U, 0> {
+    __device__ __forceinline__ static void run(float2 (&acc)[kR][kCC], const float2 (&win)[kR][kCC + G - 1], const float (&w)[G]) {
+        fma_pair<G, U, 0>(acc, win, w);
+    }
+};
 
 // load one input row into window slot SLOT
-template <int SLOT>
-__device__ __forceinline__ void load_row(float2 (&win)[kR][kWinW], uint32_t addr) {
+template <int W, int SLOT>
+__device__ __forceinline__ void load_row(float2 (&win)[kR][W], uint32_t addr) {
 #pragma unroll
-    for (int k = 0; k < kWinW; ++k) {
+    for (int k = 0; k < W; ++k) {
         if constexpr (SLOT < kR)
             win[SLOT][k].x = lds_f32(addr + 4 * k);
         else
@@ -566,72 +418,72 @@ __device__ __forceinline__ void load_row(float2 (&win)[kR][kWinW], uint32_t addr
     }
 }
 
-// Step s of a segment sweep, s mod kRows == U: fetch the new top row into the slot the previous step freed and the
-// NEXT step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate the taps
-// present in this step's vector; absent taps are skipped with warp-uniform branches.
-// Step s of a segment sweep, s mod kRows == U: fetch the new top row into the slot the previous step freed and the
-// NEXT step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate the taps
-// present in this step's vector; absent taps are skipped with warp-uniform branches.  (A fall-through chain driven by
-// per-step first/last codes was tried: the compiler's nested reconvergence scaffolding made it slower.)
-// the kGroupW weights of one step
+// the G weights of one step
+template <int G>
 struct WeightVec {
-    float4 q[kGroupW / 4];
+    float v[G];
 };
-__device__ __forceinline__ WeightVec lds_weights(uint32_t addr) {
-    WeightVec w;
-#pragma unroll
-    for (int i = 0; i < kGroupW / 4; ++i) w.q[i] = lds_v4(addr + 16u * i);
+template <int G>
+__device__ __forceinline__ WeightVec<G> lds_weights(uint32_t addr) {
+    WeightVec<G> w;
+    if constexpr (G == 2) {
+        const float2 t = lds_v2(addr);
+        w.v[0] = t.x; w.v[1] = t.y;
+    } else {
+        const float4 t = lds_v4(addr);
+        w.v[0] = t.x; w.v[1] = t.y; w.v[2] = t.z; w.v[3] = t.w;
+    }
     return w;
 }
 
-template <int U>
-__device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                           int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, WeightVec (&wv)[2]) {
-    if (s > 0) load_row<(kRows - U) % kRows>(win, tile_cb + 4u * (uint32_t)ro_next);
-    ro_next = lds_s32(rowtab + 4u * (uint32_t)max(sr0 - (s + 1), 0));    // row offset of the next step, one step ahead
-    wp += kStepBytes;
-    wv[(U + 1) & 1] = lds_weights(wp);                                    // weights of step s + 1 (zero vector past the end)
-    const WeightVec& w = wv[U & 1];
-    if (w.q[0].x != 0.0f) fma_tap<U, 0>(acc, win, w.q[0].x);
-    if (w.q[0].y != 0.0f) fma_tap<U, 1>(acc, win, w.q[0].y);
-    if (w.q[0].z != 0.0f) fma_tap<U, 2>(acc, win, w.q[0].z);
-    if (w.q[0].w != 0.0f) fma_tap<U, 3>(acc, win, w.q[0].w);
-    if constexpr (kGroupW == 8) {
-        if (w.q[kGroupW / 4 - 1].x != 0.0f) fma_tap<U, 4>(acc, win, w.q[kGroupW / 4 - 1].x);
-        if (w.q[kGroupW / 4 - 1].y != 0.0f) fma_tap<U, 5>(acc, win, w.q[kGroupW / 4 - 1].y);
-        if (w.q[kGroupW / 4 - 1].z != 0.0f) fma_tap<U, 6>(acc, win, w.q[kGroupW / 4 - 1].z);
-        if (w.q[kGroupW / 4 - 1].w != 0.0f) fma_tap<U, 7>(acc, win, w.q[kGroupW / 4 - 1].w);
-    }
+// Step s of a segment sweep, s mod kRows == U: fetch the new top row into the slot the previous step freed and the NEXT
+// step's weight vector (kRows is even, so the two weight registers simply alternate), then accumulate all G taps of this
+// step's vector.  No data-dependent control flow: absent taps carry zero weights.  The row's address comes from one of
+// four address registers (s mod 4): the skew of consecutive staged rows has period 4.
+template <int G, int U>
+__device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kCC + G - 1], uint32_t (&addr)[4], uint32_t stride4,
+                                           int& s, int nsteps, uint32_t& wp, WeightVec<G> (&wv)[2]) {
+    load_row<kCC + G - 1, (kRows - U) % kRows>(win, addr[U & 3]);
+    addr[U & 3] -= stride4;
+    wp += 4u * G;
+    wv[(U + 1) & 1] = lds_weights<G>(wp);                                 // weights of step s + 1 (zero vector past the end)
+    PairLoop<G, U, kR - 1>::run(acc, win, wv[U & 1].v);
     ++s;
     return s < nsteps;
 }
 
-// step 0 needs all kRows rows: logical row q -> slot q
-template <int Q>
-__device__ __forceinline__ void fill_window(float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab, int sr0) {
-    load_row<Q>(win, tile_cb + 4u * (uint32_t)lds_s32(rowtab + 4u * (uint32_t)(sr0 + Q)));
-    if constexpr (Q + 1 < kRows) fill_window<Q + 1>(win, tile_cb, rowtab, sr0);
-}
-
 // kRows consecutive steps = one full rotation of the window registers
-template <int U>
+template <int G, int U>
 struct SweepRound {
-    __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kWinW], uint32_t tile_cb, uint32_t rowtab,
-                                               int sr0, int& s, int nsteps, uint32_t& wp, int& ro_next, WeightVec (&wv)[2]) {
-        if (!sweep_step<U>(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) return false;
+    __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kCC + G - 1], uint32_t (&addr)[4], uint32_t stride4,
+                                               int& s, int nsteps, uint32_t& wp, WeightVec<G> (&wv)[2]) {
+        if (!sweep_step<G, U>(acc, win, addr, stride4, s, nsteps, wp, wv)) return false;
         if constexpr (U + 1 < kRows)
-            return SweepRound<U + 1>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv);
+            return SweepRound<G, U + 1>::run(acc, win, addr, stride4, s, nsteps, wp, wv);
         else
             return true;
     }
 };
+static_assert(kRows % 4 == 0, "the skew period (4 rows) must divide the window's rotation period");
 
-__device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t stage_addr, int nseg, int dy_hi, int dx_hi,
-                                              int wrow, int wcol) {
+// rows 1 .. kRows-1 of step 0's window (row 0 is step 0's own new row): logical row q -> slot q, staged row sr0 + q
+template <int W, int Q>
+__device__ __forceinline__ void fill_window(float2 (&win)[kR][W], uint32_t a0, uint32_t stride, int skew_sr0, int dskew) {
+    load_row<W, Q>(win, a0 + (uint32_t)Q * stride + 4u * (uint32_t)((skew_sr0 + Q * dskew) & 3));
+    if constexpr (Q + 1 < kRows) fill_window<W, Q + 1>(win, a0, stride, skew_sr0, dskew);
+}
+
+template <int G>
+__device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t stage_addr, int nseg, int dy_hi, int dx_hi, int shear,
+                                              int skew0, int dskew, int wrow, int wcol) {
+    constexpr int kWinW = kCC + G - 1;
     const int lane = threadIdx.x & 31;
-    const uint32_t aux = stage_addr + kHdrBytes;
-    const uint32_t rowtab = aux + kAuxBytes;
-    const uint32_t tile = rowtab + kRowTabBytes;
+    const uint32_t aux = stage_addr + kStageHdrBytes;
+    const uint32_t tile = aux + kChunkAuxBytes;
+    // a staged row further down is one output row further down in the thread's block, whose columns start `shear` further
+    // right: the window's column origin moves with the row, by a constant number of bytes per step
+    const uint32_t stride = 4u * (uint32_t)(kPitch + shear);
+    const int o1 = shear < 0 ? -(kRows - 1) * shear : 0;
     // The two compute warps that share an SM sub-partition (warp ids w and w + 4) walk the segments in opposite
     // orders: otherwise they run the same instruction sequence in lockstep and their load phases coincide.
     const bool reverse = ((threadIdx.x >> 5) & 4) != 0;
@@ -639,21 +491,26 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int sg = reverse ? nseg - 1 - sgi : sgi;
         int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, woff} as two words
-        lds_entry(aux + 8u * (uint32_t)sg, reinterpret_cast<float&>(raw0), raw1);
+        lds_entry(aux + 8u * (uint32_t)sg, raw0, raw1);
         const int seg_dx0 = (int)(short)(raw0 & 0xffff), seg_dy0 = raw0 >> 16;
         const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
-        const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
-        const uint32_t tile_cb = tile + 4u * (uint32_t)colbase;
-        const int sr0 = wrow * kRows - seg_dy0 + dy_hi;   // staged row of output row 0 at step 0
-        uint32_t wp = aux + kChunkSegBytes + (uint32_t)kStepBytes * (uint32_t)seg_woff;
-        WeightVec wv[2];
-        wv[0] = lds_weights(wp);
+        const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (G - 1) + o1 + dx_hi;
+        const int sr0 = wrow * kRows - seg_dy0 + dy_hi;    // staged row of output row 0 at step 0
+        const uint32_t a0 = tile + 4u * (uint32_t)(sr0 * kPitch + colbase);
+        const int skew_sr0 = skew0 + sr0 * dskew;           // (.. & 3) = skew of staged row sr0
+        uint32_t wp = aux + kChunkSegBytes + 4u * G * (uint32_t)seg_woff;
+        WeightVec<G> wv[2];
+        wv[0] = lds_weights<G>(wp);
         float2 win[kR][kWinW];
-        fill_window<0>(win, tile_cb, rowtab, sr0);
-        int ro_next = 0;
+        fill_window<kWinW, 1>(win, a0, stride, skew_sr0, dskew);
+        // step s loads staged row sr0 - s: address a0 - s * stride + 4 * ((skew_sr0 - s * dskew) & 3); the last term has
+        // period 4 in s, so step s uses addr[s & 3] and then moves it four steps on
+        uint32_t addr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) addr[j] = a0 - (uint32_t)j * stride + 4u * (uint32_t)((skew_sr0 - j * dskew) & 3);
         int s = 0;
 #pragma unroll 1
-        while (SweepRound<0>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) {
+        while (SweepRound<G, 0>::run(acc, win, addr, 4u * stride, s, nsteps, wp, wv)) {
         }
     }
 }
@@ -661,19 +518,20 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
 // ---------------------------------------------------------------- epilogue + store (per warp, no block barrier)
 // One staged row -> global with the fused epilogue (noise / clamp / gamma / normalize).  Kept out of line: the
 // common no-epilogue path below stays small and the register-tile code is not replicated around powf / Philox.
-// `srow` is the 16-byte-aligned start of the staged row; element x of the row sits at srow[skew + x].
-__device__ __noinline__ void store_row_epilogue(const float* srow, float* g, const float* nz_row, int wv, int skew, Epilogue ep,
+// `srow` is the 16-byte-aligned start of the staged row; element x of the row sits at srow[skew + x]; elements
+// [x_lo, x_hi) are stored.
+__device__ __noinline__ void store_row_epilogue(const float* srow, float* g, const float* nz_row, int x_lo, int x_hi, int skew, Epilogue ep,
                                                 uint64_t seed, uint64_t stream, uint64_t pbase) {
     const int lane = threadIdx.x & 31;
-    for (int k = lane; 4 * k - skew < wv; k += 32) {
+    for (int k = lane; 4 * k - skew < x_hi; k += 32) {
         const int x0 = 4 * k - skew;
         const float4 v = *reinterpret_cast<const float4*>(srow + 4 * k);
         float o[4] = {v.x, v.y, v.z, v.w};
-        const bool whole = (x0 >= 0) && (x0 + 3 < wv);
+        const bool whole = (x0 >= x_lo) && (x0 + 3 < x_hi);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + j;
-            if (x >= 0 && x < wv) {
+            if (x >= x_lo && x < x_hi) {
                 float nz = 0.f;
                 if (ep.flags & DIB_EPI_NOISE) nz = nz_row ? nz_row[x] : philox_normal(seed, stream, pbase + x);
                 o[j] = apply_epilogue_f32(o[j], ep, nz);
@@ -684,14 +542,14 @@ __device__ __noinline__ void store_row_epilogue(const float* srow, float* g, con
     }
 }
 
-// One staged row -> global without epilogue.  Element x of the row sits at srow + 4 * (skew + x).  Aligned quads
-// k0 .. k1-1 lie wholly inside [0, wv) and go out as 16-byte stores; the <= 3 elements before the first and after the
-// last whole quad are stored one per lane.  (A specialised path for full-width rows with lane-dependent roles was
-// measured 4 % slower: the divergence costs more than the saved arithmetic.)
+// One staged row -> global without epilogue.  Element x of the row sits at srow + 4 * (skew + x); elements [x_lo, x_hi)
+// are stored.  Aligned quads k0 .. k1-1 lie wholly inside the range and go out as 16-byte stores; the <= 3 elements before
+// the first and after the last whole quad are stored one per lane.
 template <bool kAffine>
-__device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int skew, int wv, int lane, float scale, float shift) {
-    const int k0 = (skew + 3) >> 2, k1 = (wv + skew) >> 2;
-    const int head = min(4 * k0 - skew, wv), tail0 = max(4 * k1 - skew, head);
+__device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int skew, int x_lo, int x_hi, int lane, float scale, float shift) {
+    const int k0 = (x_lo + skew + 3) >> 2, k1 = max((x_hi + skew) >> 2, k0);
+    const int head1 = min(4 * k0 - skew, x_hi), tail0 = max(4 * k1 - skew, head1);
+    const int nhead = head1 - x_lo;
 #pragma unroll
     for (int it = 0; it < (kWarpW + 3 + 127) / 128; ++it) {
         const int k = lane + 32 * it;
@@ -706,8 +564,8 @@ __device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int ske
             *reinterpret_cast<float4*>(g + (4 * k - skew)) = v;
         }
     }
-    const int x = lane < head ? lane : tail0 + (lane - head);
-    if (x < wv && (lane < head || x >= tail0)) {
+    const int x = lane < nhead ? x_lo + lane : tail0 + (lane - nhead);
+    if (x < x_hi && (lane < nhead || x >= tail0)) {
         float v = lds_f32(srow + 4u * (uint32_t)(skew + x));
         if (kAffine) v = fmaf(v, scale, shift);
         g[x] = v;
@@ -715,8 +573,8 @@ __device__ __forceinline__ void store_row_plain(float* g, uint32_t srow, int ske
 }
 
 // Destination rows that all start 16-byte aligned (a pitched output, e.g. the padded batch or the wrapper's own
-// allocations) need no per-row skew, no head elements and -- except in the last column tile -- no tail: a third of the
-// general store's instructions.  Row q of the pass sits unskewed at obuf + q * kOutPitch.
+// allocations) and an unsheared block need no per-row skew, no head elements and -- except in the last column tile -- no
+// tail: a third of the general store's instructions.  Row q of the pass sits unskewed at obuf + q * kOutPitch.
 template <bool kAffine>
 __device__ __forceinline__ void store_rows_aligned(const TiledImage& im, int ch, int row0, int col0, float2 (&acc)[kR][kCC],
                                                    uint32_t obuf, float scale, float shift) {
@@ -763,65 +621,16 @@ __device__ __forceinline__ void store_rows_aligned(const TiledImage& im, int ch,
     }
 }
 
-// Half-precision destination with 16-byte-aligned rows: eight values per lane and row, rounded to half once.
-template <bool kAffine>
-__device__ __forceinline__ void store_rows_aligned_half(const TiledImage& im, int ch, int row0, int col0, float2 (&acc)[kR][kCC],
-                                                        uint32_t obuf, float scale, float shift) {
-    const int lane = threadIdx.x & 31;
-    const int wv = min(kWarpW, im.W - col0);
-    const int nrows = min(kRows, im.H - row0);
-    const int n8 = wv >> 3, tail = wv & 7;
-    const bool q0 = lane < n8, qt = lane < tail;
-    __half* g = static_cast<__half*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
-    const uint32_t sts0 = obuf + 4u * (uint32_t)(kCC * lane), lds0 = obuf + 32u * (uint32_t)lane;
-#pragma unroll
-    for (int r = 0; r < kRows; r += 2) {
-        if (r >= nrows) break;
-#pragma unroll
-        for (int c = 0; c < kCC; ++c) {
-            sts_f32(sts0 + 4u * c, r < kR ? acc[r % kR][c].x : acc[r % kR][c].y);
-            sts_f32(sts0 + 4u * (kOutPitch + c), r + 1 < kR ? acc[(r + 1) % kR][c].x : acc[(r + 1) % kR][c].y);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (r + q < nrows) {
-                __half* grow = g + (int64_t)q * im.dst_rp;
-                const uint32_t l = lds0 + 4u * (uint32_t)(q * kOutPitch);
-                if (q0) {
-                    float4 a = lds_v4(l), b = lds_v4(l + 16u);
-                    if (kAffine) {
-                        a.x = fmaf(a.x, scale, shift); a.y = fmaf(a.y, scale, shift); a.z = fmaf(a.z, scale, shift); a.w = fmaf(a.w, scale, shift);
-                        b.x = fmaf(b.x, scale, shift); b.y = fmaf(b.y, scale, shift); b.z = fmaf(b.z, scale, shift); b.w = fmaf(b.w, scale, shift);
-                    }
-                    uint4 o;
-                    *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(a.x, a.y);
-                    *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(a.z, a.w);
-                    *reinterpret_cast<__half2*>(&o.z) = __floats2half2_rn(b.x, b.y);
-                    *reinterpret_cast<__half2*>(&o.w) = __floats2half2_rn(b.z, b.w);
-                    *reinterpret_cast<uint4*>(grow + 8 * lane) = o;
-                }
-                if (tail != 0 && qt) {
-                    float v = lds_f32(obuf + 4u * (uint32_t)(q * kOutPitch + 8 * n8 + lane));
-                    if (kAffine) v = fmaf(v, scale, shift);
-                    grow[8 * n8 + lane] = __float2half_rn(v);
-                }
-            }
-        }
-        __syncwarp();
-        g += 2 * im.dst_rp;
-    }
-}
-
 // Epilogue variants of the kernel: none; normalize only, applied as one FMA per pixel, x * (1/std) - mean/std (the
 // tiled kernel is not the bit-exact path, and an IEEE division per pixel would double its store cost); everything else.
 constexpr int kEpiNone = 0, kEpiAffine = 1, kEpiGeneral = 2;
 
-template <int kEpi, bool kHalf>
-__device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0,
+// `col0` is the nominal first column of the warp's block; with a sheared program output row r of the block starts at
+// col0 + shear * r - (shear > 0 ? shear * (kRows - 1) : 0) and may begin left of the image or end right of it.
+template <int kEpi>
+__device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImage& im, int ch, int row0, int col0, int shear,
                                            float2 (&acc)[kR][kCC], uint32_t obuf) {
     const int lane = threadIdx.x & 31;
-    const int wv = min(kWarpW, im.W - col0);
     Epilogue ep;
     ep.flags = im.epilogue;
     ep.noise_sd = im.noise_sd;
@@ -830,26 +639,26 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
     ep.std = im.std[ch & 3];
     const bool norm = (im.epilogue & DIB_EPI_NORMALIZE) != 0;
     const float aff_scale = norm ? 1.0f / ep.std : 1.0f, aff_shift = norm ? -ep.mean / ep.std : 0.0f;
-    if constexpr (kHalf) {
-        // the launcher only admits half images whose destination rows are 16-byte aligned and whose epilogue is affine
-        store_rows_aligned_half<kEpi == kEpiAffine>(im, ch, row0, col0, acc, obuf, aff_scale, aff_shift);
-        return;
-    }
-    if (kEpi != kEpiGeneral && im.aligned_out) {
+    if (kEpi != kEpiGeneral && im.aligned_out && shear == 0) {
         store_rows_aligned<kEpi == kEpiAffine>(im, ch, row0, col0, acc, obuf, aff_scale, aff_shift);
         return;
     }
-    float* g = static_cast<float*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0;
-    const float* nz_row = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp + col0 : nullptr;
-    uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2);
-    const uint32_t rp_lo = (uint32_t)im.dst_rp;
     const int nrows = min(kRows, im.H - row0);
+    int gcol = col0 - (shear > 0 ? shear * (kRows - 1) : 0);            // first column of row 0 of the block
+    float* g = static_cast<float*>(im.dst) + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp;   // column 0 of the row
+    const float* nz = im.noise ? im.noise + (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp : nullptr;
+    const uint32_t base_phase = (uint32_t)(reinterpret_cast<uintptr_t>(im.dst) >> 2);
+    int64_t row_elem = (int64_t)ch * im.dst_cp + (int64_t)row0 * im.dst_rp;
     // two rows per pass: accumulators -> the warp's two row buffers (each skewed so that shared and global addresses
     // agree mod 16 bytes: element x of a row sits at buffer[skew + x]), then 16-byte stores of both rows.
     // Output row q is the .x half of pair q for q < kR and the .y half of pair q - kR otherwise.
 #pragma unroll
     for (int r = 0; r < kRows; r += 2) {
-        const int skew0 = (int)(phase & 3u), skew1 = (int)((phase + rp_lo) & 3u);
+        const int gc0 = gcol, gc1 = gcol + shear;
+        const int skew0 = (int)((base_phase + (uint32_t)(row_elem + gc0)) & 3u);
+        const int skew1 = (int)((base_phase + (uint32_t)(row_elem + im.dst_rp + gc1)) & 3u);
+        const int lo0 = max(0, -gc0), hi0 = min(kWarpW, im.W - gc0);
+        const int lo1 = max(0, -gc1), hi1 = min(kWarpW, im.W - gc1);
         const uint32_t b0 = obuf, b1 = obuf + 4u * kOutPitch;
         if (r < nrows) {
 #pragma unroll
@@ -862,37 +671,40 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
                 sts_f32(b1 + 4u * (uint32_t)(skew1 + kCC * lane + c), r + 1 < kR ? acc[(r + 1) % kR][c].x : acc[(r + 1) % kR][c].y);
         }
         __syncwarp();
-        float* g1 = g + im.dst_rp;
+        float* g0 = g + gc0;
+        float* g1 = g + im.dst_rp + gc1;
         if (kEpi != kEpiGeneral) {
-            if (r < nrows) store_row_plain<kEpi == kEpiAffine>(g, b0, skew0, wv, lane, aff_scale, aff_shift);
-            if (r + 1 < nrows) store_row_plain<kEpi == kEpiAffine>(g1, b1, skew1, wv, lane, aff_scale, aff_shift);
+            if (r < nrows && hi0 > lo0) store_row_plain<kEpi == kEpiAffine>(g0, b0, skew0, lo0, hi0, lane, aff_scale, aff_shift);
+            if (r + 1 < nrows && hi1 > lo1) store_row_plain<kEpi == kEpiAffine>(g1, b1, skew1, lo1, hi1, lane, aff_scale, aff_shift);
         } else {
             const uint64_t stream = p.philox_offset + (uint64_t)im.philox_slot;
             const float* sm0 = reinterpret_cast<const float*>(__cvta_shared_to_generic(b0));
-            if (r < nrows)
-                store_row_epilogue(sm0, g, nz_row, wv, skew0, ep, p.philox_seed, stream,
-                                   ((uint64_t)ch * im.H + (row0 + r)) * im.W + col0);
-            if (r + 1 < nrows)
-                store_row_epilogue(sm0 + kOutPitch, g1, nz_row ? nz_row + im.dst_rp : nullptr, wv, skew1, ep, p.philox_seed, stream,
-                                   ((uint64_t)ch * im.H + (row0 + r + 1)) * im.W + col0);
+            if (r < nrows && hi0 > lo0)
+                store_row_epilogue(sm0, g0, nz ? nz + gc0 : nullptr, lo0, hi0, skew0, ep, p.philox_seed, stream,
+                                   ((uint64_t)ch * im.H + (row0 + r)) * im.W + gc0);
+            if (r + 1 < nrows && hi1 > lo1)
+                store_row_epilogue(sm0 + kOutPitch, g1, nz ? nz + im.dst_rp + gc1 : nullptr, lo1, hi1, skew1, ep, p.philox_seed, stream,
+                                   ((uint64_t)ch * im.H + (row0 + r + 1)) * im.W + gc1);
         }
         __syncwarp();
         g += 2 * im.dst_rp;
-        if (nz_row) nz_row += 2 * im.dst_rp;
-        phase += 2u * rp_lo;
+        if (nz) nz += 2 * im.dst_rp;
+        row_elem += 2 * im.dst_rp;
+        gcol += 2 * shear;
     }
 }
 
 // ---------------------------------------------------------------- kernel
 // kEpi selects the epilogue variant (kEpiNone / kEpiAffine / kEpiGeneral); batches without one run the leanest.
-template <int kEpi, bool kHalf>
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
     float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
-    uint64_t* full = bars;          // [2] producers -> consumers: stage loaded
+    uint64_t* full = bars;          // [2] producers -> consumers: stage loaded and patched
     uint64_t* empty = bars + 2;     // [2] consumers -> producers: stage may be refilled
-    uint64_t* landed = bars + 4;    // [2] half I/O only: the stage's bulk copies have arrived, rows may be widened
+    uint64_t* landed = bars + 4;    // [2] TMA -> producers: the stage's boxes have arrived, borders may be patched
     int* tile_slots = reinterpret_cast<int*>(bars + 6);
     const int warp = threadIdx.x >> 5;
 
@@ -903,11 +715,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (threadIdx.x == 0) {
-        // float: per producer thread one arrive.expect_tx + one cp.async arrive; half: one plain arrive after widening
-        mbar_init(&full[0], (kHalf ? 1 : 2) * kProducerWarps * 32);
-        mbar_init(&full[1], (kHalf ? 1 : 2) * kProducerWarps * 32);
-        mbar_init(&landed[0], kProducerWarps * 32);
-        mbar_init(&landed[1], kProducerWarps * 32);
+        mbar_init(&full[0], kProducerThreads);      // one cp.async-arrive per producer thread
+        mbar_init(&full[1], kProducerThreads);
+        mbar_init(&landed[0], 1);                   // one arrive.expect_tx; the boxes complete the transaction bytes
+        mbar_init(&landed[1], 1);
         mbar_init(&empty[0], kComputeWarps);
         mbar_init(&empty[1], kComputeWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -915,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     __syncthreads();
 
     // Register budget: the launch splits the register file evenly over all warps; the producer warpgroup hands most of
-    // its share back so that the compute warps can hold kR * kCC accumulators + kR * kWinW window values per thread.
+    // its share back so that the compute warps can hold kR * kCC accumulators + kR * (kCC + 3) window values per thread.
     if (warp >= kComputeWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         // ------------------------------------------------ producer warpgroup
@@ -927,23 +738,18 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         if (cur.tile >= 0) {
             decode_tile(p, cur.tile, cur);
             cur.rec = load_chunk_rec(p, cur.img, 0);
+            issue_stage(p, cur, stage_base(smem_base, 0), &landed[0], pt);
         }
+        // stage n lives in buffer n & 1.  Per iteration: look up stage n + 1; if its buffer is already free start its loads
+        // right away (memory-bound regime: two stages in flight), patch and publish stage n, else start them afterwards.
         for (int n = 0;; ++n) {
-            const int b = n & 1;
-            next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the issue below
-            const bool wait_empty = n >= 2;
-            const uint32_t empty_parity = (uint32_t)(((n >> 1) - 1) & 1);
-            // the float path waits inside issue_stage, after the row arithmetic
-            if ((kHalf || cur.tile < 0) && wait_empty) mbar_wait(&empty[b], empty_parity);
-            const StageSmem sm = stage_smem(smem, b);
+            const int b = n & 1, b1 = b ^ 1;
             if (cur.tile < 0) {
-                if (pt == 0) sm.hdr->tile = -1;
-                if constexpr (kHalf) {
-                    mbar_arrive(&full[b]);
-                } else {
-                    mbar_arrive_expect_tx(&full[b], 0);
-                    cp_async_mbar_arrive(&full[b]);
-                }
+                // no more work: publish a stop marker in the buffer stage n would have used
+                if (n >= 2) mbar_wait(&empty[b], (uint32_t)(((n >> 1) - 1) & 1));
+                if (pt == 0) reinterpret_cast<StageHdr*>(smem + (size_t)b * kStageBytes)->tile = -1;
+                __threadfence_block();
+                cp_async_mbar_arrive(&full[b]);
                 // this CTA has stopped fetching; the last CTA to get here rewinds the scheduler for the next launch
                 if (pt == 0) {
                     __threadfence();
@@ -955,10 +761,18 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
                 }
                 break;
             }
-            if constexpr (kHalf)
-                issue_stage_half(p, cur, sm, &landed[b], (uint32_t)((n >> 1) & 1), &full[b], pt);
-            else
-                issue_stage(p, cur, sm, &full[b], pt, &empty[b], empty_parity, wait_empty);
+            next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the work below
+            const uint32_t empty_parity = (uint32_t)((((n + 1) >> 1) - 1) & 1);
+            bool issued = false;
+            if (nxt.tile >= 0 && (n + 1 < 2 || __all_sync(0xffffffffu, mbar_test(&empty[b1], empty_parity)))) {     // warp-uniform
+                issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
+                issued = true;
+            }
+            finish_stage(p, cur, stage_base(smem_base, b), &landed[b], (uint32_t)((n >> 1) & 1), &full[b], pt);
+            if (nxt.tile >= 0 && !issued) {
+                mbar_wait(&empty[b1], empty_parity);
+                issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
+            }
             cur = nxt;
         }
     } else {
@@ -969,15 +783,17 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         const uint32_t obuf = smem_u32(obuf_all + warp * 2 * kOutPitch);
         for (int n = 0;; ++n) {
             const int b = n & 1;
-            const StageSmem sm = stage_smem(smem, b);
+            const uint32_t sbase = stage_base(smem_base, b);
             mbar_wait(&full[b], (n >> 1) & 1);
             StageHdr h;
             {   // explicit vector loads keep the header in registers
-                const int4 a = reinterpret_cast<const int4*>(sm.hdr)[0], b4 = reinterpret_cast<const int4*>(sm.hdr)[1];
-                const int4 c2 = reinterpret_cast<const int4*>(sm.hdr)[2];
+                const int4* hp = reinterpret_cast<const int4*>(smem + (size_t)b * kStageBytes);
+                const int4 a = hp[0], b4 = hp[1], c2 = hp[2];
                 h.tile = a.x; h.img = a.y; h.ch = a.z; h.i0 = a.w;
                 h.j0 = b4.x; h.first_chunk = b4.y; h.last_chunk = b4.z; h.dy_hi = b4.w;
-                h.dx_hi = c2.x; h.nseg = c2.y; h.wsteps = c2.z;
+                h.dx_hi = c2.x; h.nseg = c2.y; h.group_w = c2.z; h.shear = c2.w;
+                const int2 d2 = *reinterpret_cast<const int2*>(hp + 3);
+                h.skew0 = d2.x; h.dskew = d2.y;
             }
             if (h.tile < 0) break;
             if (h.first_chunk) {
@@ -988,20 +804,43 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             }
             const TiledImage& im = p.img[h.img];
             const int row0 = h.i0 + wrow * kRows, col0 = h.j0 + wcol * kWarpW;
-            const bool active = row0 < im.H && col0 < im.W;                       // warp-uniform
-            if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
+            const int pad = (kRows - 1) * (h.shear < 0 ? -h.shear : h.shear);
+            const bool active = row0 < im.H && col0 - pad < im.W;                 // warp-uniform
+            if (active) {
+                if (h.group_w == 2)
+                    compute_chunk<2>(acc, sbase, h.nseg, h.dy_hi, h.dx_hi, h.shear, h.skew0, h.dskew, wrow, wcol);
+                else
+                    compute_chunk<4>(acc, sbase, h.nseg, h.dy_hi, h.dx_hi, h.shear, h.skew0, h.dskew, wrow, wcol);
+            }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
-            if (h.last_chunk && active) store_rows<kEpi, kHalf>(p, im, h.ch, row0, col0, acc, obuf);
+            if (h.last_chunk && active) store_rows<kEpi>(p, im, h.ch, row0, col0, h.shear, acc, obuf);
         }
     }
 }
 
 // ---------------------------------------------------------------- host launcher
-int tiled_tile_counts(int H, int W, int* tiles_y, int* tiles_x) {
+int tiled_tile_counts(int H, int W, int shear, int* tiles_y, int* tiles_x) {
+    const int pad = (kRows - 1) * (shear < 0 ? -shear : shear);
     *tiles_y = (H + kTH - 1) / kTH;
-    *tiles_x = (W + kTW - 1) / kTW;
+    *tiles_x = (W + pad + kTW - 1) / kTW;
     return *tiles_y * *tiles_x;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;      // resolved once per process through the runtime (no link against libcuda)
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
@@ -1012,12 +851,19 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     DIB_CUDA(cudaGetDevice(&dev));
     if (attr_set_dev != dev) {
         DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set_dev = dev;
+    }
+    if (io_dtype != DIB_F32) {
+        set_error("dib_blur_batch: the tiled kernel takes float32 images");
+        return DIB_ERR_UNSUPPORTED;
+    }
+    const EncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) {
+        set_error("dib_blur_batch: cuTensorMapEncodeTiled is not available from this driver");
+        return DIB_ERR_CUDA;
     }
     TiledParams p;
     int total = 0;
@@ -1036,27 +882,13 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         t.C = im.C;
         t.H = im.H;
         t.W = im.W;
-        const int per_ch = tiled_tile_counts(im.H, im.W, &t.tiles_y, &t.tiles_x);
+        t.shear = m.prog_shear;
+        const int per_ch = tiled_tile_counts(im.H, im.W, t.shear, &t.tiles_y, &t.tiles_x);
         t.first_tile = total;
         t.psf_index = im.psf_index;
         t.nchunks = m.prog_chunks;
         t.epilogue = im.epilogue;
         t.zero_pad = (im.pad_mode == DIB_PAD_ZERO128);
-        // A PSF whose program is one chunk: taps.cu builds that chunk from the support's bounding box alone (first group at
-        // xmin, rows ymin .. ymax, data right after the chunk table), so the record is reproduced here from the host summary.
-        t.rec0_valid = 0;
-        if (m.prog_chunks == 1) {
-            const int centre = 63;
-            const int g_last = (m.xmax - m.xmin) / kGroupW;
-            t.rec0.dy_lo = (int16_t)(m.ymin - centre);
-            t.rec0.dy_hi = (int16_t)(m.ymax - centre);
-            t.rec0.dx_lo = (int16_t)(m.xmin - centre);
-            t.rec0.dx_hi = (int16_t)(m.xmin - centre + g_last * kGroupW + kGroupW - 1);
-            t.rec0.nseg = (int16_t)m.prog_segs;
-            t.rec0.wsteps = (int16_t)m.prog_steps;
-            t.rec0.data_off = (int32_t)kProgHeaderBytes;
-            t.rec0_valid = 1;
-        }
         t.aligned_out = ((reinterpret_cast<uintptr_t>(im.dst) & 15u) == 0 && (im.dst_row_pitch & 3) == 0 && (im.dst_chan_pitch & 3) == 0) ? 1 : 0;
         if ((t.epilogue & DIB_EPI_NOISE) && !(t.epilogue & DIB_EPI_PHILOX) && t.noise == nullptr) t.epilogue &= ~DIB_EPI_NOISE;
         any_epi |= (t.epilogue != 0);
@@ -1068,6 +900,29 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
             t.mean[c] = im.mean[c];
             t.std[c] = im.std[c];
         }
+        // 1-D tensor map over the image's elements: base = the 16-byte-aligned address at or below src, extent = up to the
+        // image's last element; a box is 256 consecutive elements starting at any coordinate (zero fill outside)
+        const uintptr_t src_addr = reinterpret_cast<uintptr_t>(im.src);
+        const uintptr_t base = src_addr & ~uintptr_t(15);
+        t.src_off = (int)((src_addr - base) >> 2);
+        const uint64_t span = (uint64_t)t.src_off + (uint64_t)(im.C - 1) * (uint64_t)im.src_chan_pitch +
+                              (uint64_t)(im.H - 1) * (uint64_t)im.src_row_pitch + (uint64_t)im.W;
+        if (span >= (1ull << 31)) {
+            set_error("dib_blur_batch: image %d spans %llu elements, more than a 1-D tensor map's signed coordinates address", order[k],
+                      (unsigned long long)span);
+            return DIB_ERR_UNSUPPORTED;
+        }
+        const cuuint64_t gdim[1] = {(cuuint64_t)span};
+        const cuuint64_t gstride[1] = {0};
+        const cuuint32_t box[1] = {kBoxElems};
+        const cuuint32_t estride[1] = {1};
+        const CUresult cr = encode(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, reinterpret_cast<void*>(base), gdim, gstride, box, estride,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("dib_blur_batch: cuTensorMapEncodeTiled failed with %d for image %d", (int)cr, order[k]);
+            return DIB_ERR_CUDA;
+        }
         total += per_ch * im.C;
     }
     p.prog = prog;
@@ -1076,7 +931,10 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_seed = seed;
     p.philox_offset = offset;
     p.sched = sched;
-    p.overlap_prev = overlap_prev ? 1 : 0;
+    // Overlapped launches share SMs only while the earlier grid drains: with one CTA per SM and a full grid at most two
+    // launches are ever co-resident, which the four scheduler slots cover.  A grid smaller than the machine could be
+    // co-resident with many successors, so it always orders itself after its predecessor.
+    p.overlap_prev = (overlap_prev && total >= sm_count) ? 1 : 0;
     const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
     // launched with the programmatic-stream-serialization attribute: the kernel itself decides (griddepcontrol.wait)
     // whether it orders itself after the previous launch
@@ -1090,21 +948,12 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (io_dtype == DIB_F16) {
-        if (any_general) {
-            set_error("dib_blur_batch: half images with a noise / clamp / gamma epilogue do not take the tiled kernel");
-            return DIB_ERR_UNSUPPORTED;
-        }
-        if (any_epi)
-            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, true>, p));
-        else
-            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, true>, p));
-    } else if (any_general) {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiGeneral, false>, p));
+    if (any_general) {
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiGeneral>, p));
     } else if (any_epi) {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, false>, p));
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine>, p));
     } else {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, false>, p));
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone>, p));
     }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;

@@ -30,39 +30,82 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 // ---- tap set layout (see include/dib.h) ----
-// Tiled-kernel program of one PSF (built by taps.cu, executed by blur_tiled.cu).  The PSF support is cut into
-// groups of kGroupW columns; a SEGMENT is one group's run of rows [dy0, dy0 + nsteps) with one kGroupW-wide weight
-// vector per row ("step"; zero where the PSF has no tap -- the kernel skips those with uniform branches).  Segments
-// are packed into CHUNKS whose tap extents are bounded (rows <= kChunkHaloRows, columns <= kChunkGroups groups) so that
-// tile + halo of any chunk fits the kernel's fixed shared-memory stage, whatever the PSF's overall extent.
-#ifndef DIB_GW
-#define DIB_GW 4
+// Geometry of the tiled kernel's register tiling (blur_tiled.cu); the program builder (taps.cu) shares it because the
+// extents of a program chunk are bounded by what one shared-memory stage of the kernel holds.
+#ifndef DIB_R
+#define DIB_R 4
 #endif
-constexpr int kGroupW = DIB_GW;         // PSF columns per group (kGroupW / 4 float4 of weights per step)
-constexpr int kChunkGroups = 20 / kGroupW;   // groups per chunk  -> column halo <= 19 (GW 4) / 15 (GW 8)
-static_assert(kGroupW == 4 || kGroupW == 8, "weight vectors are read as float4");
-constexpr int kChunkHaloRows = 17;      // dy_hi - dy_lo per chunk
-constexpr int kProgMaxChunks = 32;
+#ifndef DIB_WARP_ROWS
+#define DIB_WARP_ROWS 4
+#endif
+#ifndef DIB_WARP_COLS
+#define DIB_WARP_COLS 2
+#endif
+constexpr int kR = DIB_R;                   // row pairs per thread (rows r and r + kR share 64-bit accumulators: FFMA2)
+constexpr int kRows = 2 * kR;               // output rows per thread = rotation period of the register window
+constexpr int kCC = 7;                      // output columns per thread (odd lane stride: conflict-free scalar LDS)
+constexpr int kWarpW = 32 * kCC;            // 224 output columns per warp
+constexpr int kWarpRows = DIB_WARP_ROWS;    // compute warps are arranged kWarpRows x kWarpCols over a tile
+constexpr int kWarpCols = DIB_WARP_COLS;
+constexpr int kComputeWarps = kWarpRows * kWarpCols;
+constexpr int kTH = kWarpRows * kRows;      // output rows per tile
+constexpr int kTW = kWarpCols * kWarpW;     // output columns per tile
+constexpr int kPitch = 512;                 // floats per staged row: two 256-element TMA boxes
+constexpr int kOutPitch = kWarpW + 4;       // one staged output row of a warp (skew <= 3)
+constexpr int kStageHdrBytes = 64;
+// Tiled-kernel program of one PSF (built by taps.cu, executed by blur_tiled.cu).  The PSF support is SHEARED by `shear`
+// columns per row (x' = x - shear * (y - ymin): a slanted motion streak becomes near-vertical) and cut into GROUPS of
+// `group_w` sheared columns (2 or 4).  A SEGMENT is one group's run of rows [dy0, dy0 + nsteps) with one group_w-wide
+// weight vector per row ("step"); the kernel executes every step DENSELY -- all group_w taps, zero weight where the PSF
+// has none -- so the sweep has no data-dependent branches.  Segments are packed into CHUNKS (a band of neighbouring groups
+// x a window of rows) whose true tap extents fit one shared-memory stage: rows <= kChunkTapRows, columns <= kPitch - kTW
+// minus what the shear costs.
+constexpr int kChunkAuxBytes = 2240;        // segment records + weight vectors of one chunk (stage header + aux = 18 * 128 B)
+constexpr int kStageBytesFor(int rows) { return kStageHdrBytes + kChunkAuxBytes + rows * kPitch * 4; }
+constexpr int kSmemBudget = 232448 - 128;   // 227 KB per CTA minus barriers / ticket slots
+constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;
+constexpr int kRowsMax = (kSmemBudget - kOutBufBytes - 2 * (kStageHdrBytes + kChunkAuxBytes)) / (2 * kPitch * 4);   // staged rows
+constexpr int kChunkTapRows = kRowsMax - kTH + 1;      // PSF rows one chunk may span (dy_hi - dy_lo + 1)
+static_assert(kChunkTapRows >= 8, "tile too tall for the shared-memory stage");
+constexpr int kShearMax = (kRows <= 6) ? 2 : 1;       // |shear|: (kRows - 1) * |shear| extra columns per tile row band
+constexpr int kChunkSegSlots = 12;          // segments (groups) per chunk
+constexpr int kChunkSegBytes = kChunkSegSlots * 8;
+constexpr int kChunkMaxCols = 24;           // sheared columns per band (kChunkSegSlots groups of 2, or 6 of 4)
+constexpr int kChunkMaxWeightBytes = kChunkAuxBytes - kChunkSegBytes - 16;   // weight vectors (+ one zero vector past the end)
+static_assert(kChunkMaxCols * kChunkTapRows * 4 <= kChunkMaxWeightBytes, "chunk weights must fit the stage's aux area");
+constexpr int kProgMaxChunks = 48;
+// columns of halo a chunk may need: true dx extent + the shear's per-band parallelogram + the <= 3 elements a staged row
+// is skewed by (TMA boxes start 16-byte aligned in global memory) must fit kPitch - kTW
+__host__ __device__ constexpr int chunk_col_span(int shear) { return kPitch - kTW - 3 - (kRows - 1) * (shear < 0 ? -shear : shear); }
+// sheared columns per band such that any kChunkTapRows-row chunk of the band keeps its true dx extent within the stage
+__host__ __device__ constexpr int band_cols(int shear) {
+    const int a = shear < 0 ? -shear : shear;
+    const int c = chunk_col_span(shear) + 1 - (kChunkTapRows - 1) * a;
+    return c < kChunkMaxCols ? c : kChunkMaxCols;
+}
+static_assert(band_cols(kShearMax) >= 4 && band_cols(-kShearMax) >= 4, "shear leaves no room for a group");
 struct SegRec {         // 8 bytes
-    int16_t dx0;        // first tap column of the group, relative to the PSF centre (tap dx = x - centre)
+    int16_t dx0;        // tap column of the group's first column at step 0, relative to the PSF centre (dx = x - centre);
+                        // at step s the group covers dx0 + shear * s .. + group_w - 1
     int16_t dy0;        // first tap row of the run, relative to the centre
     int16_t nsteps;     // rows in the run
     int16_t woff;       // index of the run's first weight vector inside the chunk's weight array
 };
 struct ChunkRec {       // 16 bytes
     int16_t dy_lo, dy_hi;   // tap row range of the chunk (relative to the centre)
-    int16_t dx_lo, dx_hi;   // tap column range: first group's dx0 .. last group's dx0 + kGroupW - 1
-    int16_t nseg;           // segments in the chunk (<= kChunkGroups)
+    int16_t dx_lo, dx_hi;   // true tap column range over all steps of all segments (including zero-weight group columns)
     int16_t wsteps;         // weight vectors in the chunk
-    int32_t data_off;       // byte offset of the chunk's data block inside the PSF's program section
+    uint8_t nseg;           // segments in the chunk (<= kChunkSegSlots)
+    int8_t shear;           // columns per row the groups move (same for every chunk of a PSF)
+    uint8_t group_w;        // 2 or 4
+    uint8_t pad;
+    uint16_t data_off16;    // offset of the chunk's data block inside the PSF's program section, in 16-byte units
 };
-// chunk data block: SegRec slots (48 B, fixed) then float4[wsteps] (+ one zero vector: the kernel prefetches one ahead)
-constexpr int kChunkSegBytes = 48;
-constexpr int kChunkMaxSteps = kChunkGroups * (kChunkHaloRows + 1);                       // 90
-constexpr int kStepBytes = 4 * kGroupW;                                                    // one weight vector
-constexpr int kChunkDataMax = kChunkSegBytes + kStepBytes * (kChunkMaxSteps + 1);
-constexpr size_t kProgHeaderBytes = sizeof(ChunkRec) * kProgMaxChunks;                    // 512
-constexpr size_t kProgDataBytes = 16384;
+static_assert(sizeof(ChunkRec) == 16 && sizeof(SegRec) == 8, "program records are read as vectors");
+// chunk data block: SegRec slots (kChunkSegBytes, fixed) then float[wsteps + 1][group_w] (the last vector is zero: the
+// kernel prefetches one vector ahead)
+constexpr size_t kProgHeaderBytes = sizeof(ChunkRec) * kProgMaxChunks;                    // 768
+constexpr size_t kProgDataBytes = 32768;
 constexpr size_t kProgBytes = kProgHeaderBytes + kProgDataBytes;
 
 // Work-distribution words of the tiled kernel (self-resetting, see blur_tiled.cu)

@@ -74,8 +74,21 @@ __device__ inline int block_min_int(int v, int* sh) {
     return t;
 }
 
-constexpr int kMaxBands = (32 + kChunkGroups - 1) / kChunkGroups;   // <= 32 groups of kGroupW columns in a 128-wide PSF
-constexpr int kBandMaxChunks = 8;                                   // 128 rows / (kChunkHaloRows + 1) rounded up
+constexpr int kMaxGroups = 192;       // sheared groups of one PSF (support width + shear drift, in groups of 2)
+constexpr int kMaxBands = 64;
+constexpr int kBandMaxChunks = 128 / kChunkTapRows + 2;
+constexpr int kNumShears = 2 * kShearMax + 1;
+constexpr int kNumCand = 2 * kNumShears;          // group width 2 or 4 x shear -kShearMax .. kShearMax
+
+// Modelled cost (cycles of one compute warp) of one dense step / one window fill of a segment, for ranking the
+// candidates: a step is bound by its 2 * G * kR * kCC FMA-pipe cycles or by the shared-memory traffic of its window row
+// (4 warps share the load pipe), a fill is shared-memory traffic only.
+__host__ __device__ constexpr int step_cost(int G) {
+    const int fma = 2 * G * kR * kCC, lds = 4 * (kCC + G);
+    return (fma > lds ? fma : lds) + 4;
+}
+__host__ __device__ constexpr int fill_cost(int G) { return 4 * (kRows - 1) * (kCC + G - 1) + 60; }
+constexpr int kChunkCost = 250;
 
 // first set bit at position >= from in a 128-bit mask (4 words, bit y of word y >> 5), or -1
 __device__ inline int mask_first_from(const unsigned* m, int from) {
@@ -122,13 +135,14 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ int sh_i[kCompactThreads / 32];
     __shared__ int sh_warp_count[kCompactThreads / 32];
     __shared__ int sh_running;
-    __shared__ unsigned sh_occ[32 * 4];
+    __shared__ unsigned sh_occ[kMaxGroups * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
-    __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
-    __shared__ ChunkRec sh_band_chunks[kMaxBands * kBandMaxChunks];
-    __shared__ SegRec sh_band_segs[kMaxBands * kBandMaxChunks * kChunkGroups];
-    __shared__ int sh_band_count[kMaxBands];
-    __shared__ int sh_nchunks, sh_nsegs, sh_total_steps;
+    __shared__ SegRec sh_segs[kProgMaxChunks * kChunkSegSlots];
+    __shared__ int sh_band_count[kMaxBands], sh_band_base[kMaxBands];
+    __shared__ int sh_first[kNumCand][kMaxGroups], sh_last[kNumCand][kMaxGroups];
+    __shared__ int sh_xpmin[kNumShears], sh_xpmax[kNumShears];
+    __shared__ unsigned long long sh_cost[kNumCand];
+    __shared__ int sh_nchunks, sh_nsegs, sh_total_steps, sh_choice;
 
     const int n = blockIdx.x;
     if (n == 0 && threadIdx.x == 0) {
@@ -229,7 +243,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     sxx = block_sum_ll(sxx, sh_ll);
     sxy = block_sum_ll(sxy, sh_ll);
 
-    // 3. chunked column-group program for the tiled kernel (layout in dib_common.cuh, consumer blur_tiled.cu)
+    // 3. program for the tiled kernel: dense sheared column groups (layout in dib_common.cuh, consumer blur_tiled.cu)
     const int centre = side > 129 ? 127 : 63;
     int flags = 0;
     if (count > max_taps) flags |= DIB_META_TRUNCATED;
@@ -239,145 +253,251 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     // (never produced by the centred generator) stay on the generic kernel, which restates the wrap exactly.
     const bool want_prog = side <= 129 && count > 0 && ymax <= 126 && xmax <= 126;
     if (tid == 0) {
-        sh_nchunks = 0;
+        sh_nchunks = -1;
         sh_nsegs = 0;
         sh_total_steps = 0;
+        sh_choice = -1;
     }
+    int prog_G = 0, prog_k = 0;
     __syncthreads();
     if (want_prog) {
-        const int ngroups = (xmax - xmin + kGroupW) / kGroupW;   // <= 32 for side <= 129
         const int nrows_box = ymax - ymin + 1;
-        // 3a. per group: bitmask of the PSF rows holding a tap in the group's columns (rows 0..127 -> 4 words)
-        for (int k = tid; k < ngroups * 4; k += kCompactThreads) sh_occ[k] = 0u;
-        __syncthreads();
-        for (int k = tid; k < ngroups * nrows_box; k += kCompactThreads) {
-            const int g = k / nrows_box, y = ymin + k % nrows_box;
-            bool any = false;
-            for (int e = 0; e < kGroupW; ++e) {
-                const int x = xmin + g * kGroupW + e;
-                if (x < side) {
-                    const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                    const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
-                    any |= (w != 0.0f);
-                }
-            }
-            if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
+        // 3a. rank the candidates (group width 2 / 4) x (shear -kShearMax .. kShearMax) by a cost model: per sheared group
+        //     the span of rows it occupies -> dense steps, window fills and chunks.
+        if (tid < kNumShears) {
+            sh_xpmin[tid] = 1 << 20;
+            sh_xpmax[tid] = -(1 << 20);
+        }
+        if (tid < kNumCand) sh_cost[tid] = 0ull;
+        for (int k = tid; k < kNumCand * kMaxGroups; k += kCompactThreads) {
+            (&sh_first[0][0])[k] = 1 << 20;
+            (&sh_last[0][0])[k] = -1;
         }
         __syncthreads();
-        // 3b. cut the support into chunks of segments: one thread per band of kChunkGroups groups walks that band's rows
-        //     with 128-bit masks (find-first-set), then thread 0 concatenates the bands' chunk lists in band order
-        const int nbands = (ngroups + kChunkGroups - 1) / kChunkGroups;
-        if (tid < nbands) {
-            const int g0 = tid * kChunkGroups, g1 = min(g0 + kChunkGroups, ngroups);
-            unsigned band[4] = {0u, 0u, 0u, 0u};
-            for (int g = g0; g < g1; ++g)
-                for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
-            int cursor = ymin, nb = 0;
-            while (nb < kBandMaxChunks) {
-                int y0 = mask_first_from(band, cursor);
-                if (y0 < 0) break;
-                const int y1 = min(y0 + kChunkHaloRows, ymax);
-                ChunkRec c;
-                int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
-                for (int g = g0; g < g1; ++g) {
-                    int f, l;
-                    mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
-                    if (f < 0) continue;
-                    SegRec sg;
-                    sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
-                    sg.dy0 = (int16_t)(f - centre);
-                    sg.nsteps = (int16_t)(l - f + 1);
-                    sg.woff = 0;
-                    lo = min(lo, f - centre);
-                    hi = max(hi, l - centre);
-                    xlo = min(xlo, (int)sg.dx0);
-                    xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
-                    sh_band_segs[(tid * kBandMaxChunks + nb) * kChunkGroups + nseg] = sg;
-                    ++nseg;
+        for (int i = tid; i < cells; i += kCompactThreads) {
+            const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
+            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            if (w != 0.0f) {
+                const int y = i / side, x = i - y * side;
+#pragma unroll
+                for (int q = 0; q < kNumShears; ++q) {
+                    const int xp = x - (q - kShearMax) * (y - ymin);
+                    atomicMin(&sh_xpmin[q], xp);
+                    atomicMax(&sh_xpmax[q], xp);
                 }
-                c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
-                c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
-                c.nseg = (int16_t)nseg; c.wsteps = 0;
-                c.data_off = 0;
-                sh_band_chunks[tid * kBandMaxChunks + nb] = c;
-                ++nb;
-                cursor = y1 + 1;
             }
-            // more rows left than kBandMaxChunks chunks can cover: no program (the generic kernel takes the PSF)
-            sh_band_count[tid] = (nb == kBandMaxChunks && mask_first_from(band, cursor) >= 0) ? -1 : nb;
+        }
+        __syncthreads();
+        for (int i = tid; i < cells; i += kCompactThreads) {
+            const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
+            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            if (w != 0.0f) {
+                const int y = i / side, x = i - y * side;
+#pragma unroll
+                for (int q = 0; q < kNumShears; ++q) {
+                    const int xp = x - (q - kShearMax) * (y - ymin) - sh_xpmin[q];
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int g = xp >> (gi + 1);               // group width 2 << gi
+                        if (g < kMaxGroups) {
+                            atomicMin(&sh_first[gi * kNumShears + q][g], y);
+                            atomicMax(&sh_last[gi * kNumShears + q][g], y);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < kNumCand * kMaxGroups; k += kCompactThreads) {
+            const int cand = k / kMaxGroups, g = k - cand * kMaxGroups;
+            const int gi = cand / kNumShears, q = cand - gi * kNumShears, G = 2 << gi;
+            const int ngroups = ((sh_xpmax[q] - sh_xpmin[q]) >> (gi + 1)) + 1;
+            unsigned long long c = 0ull;
+            if (ngroups > kMaxGroups) {
+                c = g == 0 ? (1ull << 40) : 0ull;                    // candidate does not fit the builder's tables
+            } else if (g < ngroups) {
+                const int f = sh_first[cand][g], l = sh_last[cand][g];
+                if (l >= f) {
+                    const int span = l - f + 1;
+                    c = (unsigned long long)(span * step_cost(G) + ((span + kChunkTapRows - 1) / kChunkTapRows) * fill_cost(G));
+                }
+                if (g == 0) {       // staging cost: bands x row windows
+                    const int nb = band_cols(q - kShearMax) / G;
+                    c += (unsigned long long)(((ngroups + nb - 1) / nb) * ((nrows_box + kChunkTapRows - 1) / kChunkTapRows) * kChunkCost);
+                }
+            }
+            if (c) atomicAdd(&sh_cost[cand], c);
         }
         __syncthreads();
         if (tid == 0) {
-            int nchunks = 0, nsegs = 0;
-            bool ok = true;
-            for (int bnd = 0; bnd < nbands && ok; ++bnd) {
-                const int nb = sh_band_count[bnd];
-                if (nb < 0 || nchunks + nb > kProgMaxChunks) { ok = false; break; }
-                for (int k = 0; k < nb; ++k) {
-                    sh_chunks[nchunks] = sh_band_chunks[bnd * kBandMaxChunks + k];
-                    for (int q = 0; q < kChunkGroups; ++q)
-                        sh_segs[nchunks * kChunkGroups + q] = sh_band_segs[(bnd * kBandMaxChunks + k) * kChunkGroups + q];
-                    nsegs += sh_chunks[nchunks].nseg;
-                    ++nchunks;
-                }
-            }
-            sh_nchunks = ok ? nchunks : -1;
-            sh_nsegs = nsegs;
+            int bestc = 0;
+            for (int c = 1; c < kNumCand; ++c)
+                if (sh_cost[c] < sh_cost[bestc]) bestc = c;
+            sh_choice = bestc;
         }
         __syncthreads();
-        int nchunks = sh_nchunks;
-        // 3c. offsets: weight vectors of a chunk's segments are laid out back to back
-        if (nchunks > 0) {
-            if (tid == 0) {
-                int data_off = (int)kProgHeaderBytes, total_steps = 0;
-                bool ok = true;
-                for (int ci = 0; ci < nchunks && ok; ++ci) {
-                    int nw = 0;
-                    for (int sgi = 0; sgi < sh_chunks[ci].nseg; ++sgi) {
-                        sh_segs[ci * kChunkGroups + sgi].woff = (int16_t)nw;
-                        nw += sh_segs[ci * kChunkGroups + sgi].nsteps;
+        // 3b-3d. build with the chosen candidate; if it overflows a table, once more with unsheared groups of 4
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const int cand = attempt == 0 ? sh_choice : (1 * kNumShears + kShearMax);
+            const int gi = cand / kNumShears, q = cand - gi * kNumShears;
+            const int G = 2 << gi, shear = q - kShearMax;
+            const int xp0 = sh_xpmin[q];
+            const int ngroups = ((sh_xpmax[q] - xp0) >> (gi + 1)) + 1;
+            const int nb = band_cols(shear) / G;                     // groups per band
+            const int nbands = (ngroups + nb - 1) / nb;
+            bool fits = ngroups <= kMaxGroups && nbands <= kMaxBands;
+            __syncthreads();
+            if (fits) {
+                // per group: bitmask of the PSF rows holding a tap in the group's (sheared) columns
+                for (int k = tid; k < ngroups * 4; k += kCompactThreads) sh_occ[k] = 0u;
+                __syncthreads();
+                for (int k = tid; k < ngroups * nrows_box; k += kCompactThreads) {
+                    const int g = k / nrows_box, y = ymin + k % nrows_box;
+                    bool any = false;
+                    for (int e = 0; e < G; ++e) {
+                        const int x = xp0 + g * G + shear * (y - ymin) + e;
+                        if (x >= 0 && x < side) {
+                            const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
+                            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                            any |= (w != 0.0f);
+                        }
                     }
-                    total_steps += nw;
-                    const int bytes = kChunkSegBytes + kStepBytes * (nw + 1);
-                    if (nw > kChunkMaxSteps || data_off + bytes > (int)kProgBytes) { ok = false; break; }
-                    sh_chunks[ci].wsteps = (int16_t)nw;
-                    sh_chunks[ci].data_off = data_off;
-                    data_off += bytes;
+                    if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
                 }
-                if (!ok) sh_nchunks = -1;
-                sh_total_steps = total_steps;
+                __syncthreads();
+                // one thread per band walks the band's rows in windows of kChunkTapRows: pass 0 counts the chunks, pass 1
+                // (after a prefix sum over the bands) writes chunk and segment records
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (tid < nbands) {
+                        const int g0 = tid * nb, g1 = min(g0 + nb, ngroups);
+                        unsigned band[4] = {0u, 0u, 0u, 0u};
+                        for (int g = g0; g < g1; ++g)
+                            for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
+                        int cursor = ymin, nbc = 0;
+                        const int base = pass ? sh_band_base[tid] : 0;
+                        while (true) {
+                            const int y0 = mask_first_from(band, cursor);
+                            if (y0 < 0) break;
+                            const int y1 = min(y0 + kChunkTapRows - 1, ymax);
+                            if (pass) {
+                                ChunkRec c;
+                                int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
+                                for (int g = g0; g < g1; ++g) {
+                                    int f, l;
+                                    mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
+                                    if (f < 0) continue;
+                                    SegRec sg;
+                                    const int d0 = xp0 + g * G + shear * (f - ymin) - centre, d1 = d0 + shear * (l - f);
+                                    sg.dx0 = (int16_t)d0;
+                                    sg.dy0 = (int16_t)(f - centre);
+                                    sg.nsteps = (int16_t)(l - f + 1);
+                                    sg.woff = 0;
+                                    lo = min(lo, f - centre);
+                                    hi = max(hi, l - centre);
+                                    xlo = min(xlo, min(d0, d1));
+                                    xhi = max(xhi, max(d0, d1) + G - 1);
+                                    sh_segs[(base + nbc) * kChunkSegSlots + nseg] = sg;
+                                    ++nseg;
+                                }
+                                c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
+                                c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
+                                c.wsteps = 0;
+                                c.nseg = (uint8_t)nseg;
+                                c.shear = (int8_t)shear;
+                                c.group_w = (uint8_t)G;
+                                c.pad = 0;
+                                c.data_off16 = 0;
+                                sh_chunks[base + nbc] = c;
+                            }
+                            ++nbc;
+                            cursor = y1 + 1;
+                        }
+                        if (!pass) sh_band_count[tid] = nbc;
+                    }
+                    __syncthreads();
+                    if (!pass) {
+                        if (tid == 0) {
+                            int total = 0;
+                            for (int bnd = 0; bnd < nbands; ++bnd) {
+                                sh_band_base[bnd] = total;
+                                total += sh_band_count[bnd];
+                            }
+                            sh_nchunks = total <= kProgMaxChunks ? total : -1;
+                        }
+                        __syncthreads();
+                        if (sh_nchunks < 0) break;                      // uniform: every thread reads the same word
+                    }
+                }
+            } else if (tid == 0) {
+                sh_nchunks = -1;
             }
             __syncthreads();
-            nchunks = sh_nchunks;
-        }
-        // 3d. write chunk records, segment records and weight vectors
-        if (nchunks > 0) {
-            for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
-            for (int ci = 0; ci < nchunks; ++ci) {
-                const ChunkRec c = sh_chunks[ci];
-                SegRec* seg_out = reinterpret_cast<SegRec*>(my_prog + c.data_off);
-                float* wout = reinterpret_cast<float*>(my_prog + c.data_off + kChunkSegBytes);
-                if (tid < kChunkSegBytes / (int)sizeof(SegRec)) {
-                    SegRec sg;
-                    sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.woff = 0;
-                    if (tid < c.nseg) sg = sh_segs[ci * kChunkGroups + tid];
-                    seg_out[tid] = sg;
-                }
-                if (tid < kGroupW) wout[c.wsteps * kGroupW + tid] = 0.0f;     // the vector the kernel prefetches past the end
-                for (int sgi = 0; sgi < c.nseg; ++sgi) {
-                    const SegRec sg = sh_segs[ci * kChunkGroups + sgi];
-                    for (int k = tid; k < sg.nsteps * kGroupW; k += kCompactThreads) {
-                        const int step = k / kGroupW, e = k % kGroupW;
-                        const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
-                        float w = 0.0f;
-                        if (x < side) {
-                            const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                            w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            int nchunks = sh_nchunks;
+            // offsets: weight vectors of a chunk's segments are laid out back to back
+            if (nchunks > 0) {
+                if (tid == 0) {
+                    int data_off = (int)kProgHeaderBytes, total_steps = 0, nsegs = 0;
+                    bool ok = true;
+                    for (int ci = 0; ci < nchunks && ok; ++ci) {
+                        int nw = 0;
+                        for (int sgi = 0; sgi < sh_chunks[ci].nseg; ++sgi) {
+                            sh_segs[ci * kChunkSegSlots + sgi].woff = (int16_t)nw;
+                            nw += sh_segs[ci * kChunkSegSlots + sgi].nsteps;
                         }
-                        wout[(sg.woff + step) * kGroupW + e] = w;
+                        total_steps += nw;
+                        nsegs += sh_chunks[ci].nseg;
+                        const int bytes = (kChunkSegBytes + 4 * G * (nw + 1) + 15) & ~15;
+                        const ChunkRec& c = sh_chunks[ci];
+                        if (4 * G * (nw + 1) > kChunkMaxWeightBytes + 16 || data_off + bytes > (int)kProgBytes ||
+                            c.dx_hi - c.dx_lo > chunk_col_span(shear) || c.dy_hi - c.dy_lo >= kChunkTapRows) {
+                            ok = false;
+                            break;
+                        }
+                        sh_chunks[ci].wsteps = (int16_t)nw;
+                        sh_chunks[ci].data_off16 = (uint16_t)(data_off >> 4);
+                        data_off += bytes;
+                    }
+                    if (!ok) sh_nchunks = -1;
+                    sh_total_steps = total_steps;
+                    sh_nsegs = nsegs;
+                }
+                __syncthreads();
+                nchunks = sh_nchunks;
+            }
+            if (nchunks > 0) {
+                // write chunk records, segment records and weight vectors
+                for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
+                for (int ci = 0; ci < nchunks; ++ci) {
+                    const ChunkRec c = sh_chunks[ci];
+                    const size_t off = (size_t)c.data_off16 * 16;
+                    SegRec* seg_out = reinterpret_cast<SegRec*>(my_prog + off);
+                    float* wout = reinterpret_cast<float*>(my_prog + off + kChunkSegBytes);
+                    if (tid < kChunkSegSlots) {
+                        SegRec sg;
+                        sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.woff = 0;
+                        if (tid < c.nseg) sg = sh_segs[ci * kChunkSegSlots + tid];
+                        seg_out[tid] = sg;
+                    }
+                    if (tid < G) wout[c.wsteps * G + tid] = 0.0f;     // the vector the kernel prefetches past the end
+                    for (int sgi = 0; sgi < c.nseg; ++sgi) {
+                        const SegRec sg = sh_segs[ci * kChunkSegSlots + sgi];
+                        for (int k = tid; k < sg.nsteps * G; k += kCompactThreads) {
+                            const int step = k / G, e = k - step * G;
+                            const int x = sg.dx0 + centre + shear * step + e, y = sg.dy0 + centre + step;
+                            float w = 0.0f;
+                            if (x >= 0 && x < side) {
+                                const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
+                                w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                            }
+                            wout[(sg.woff + step) * G + e] = w;
+                        }
                     }
                 }
+                prog_G = G;
+                prog_k = shear;
+                break;
             }
+            if (attempt == 0 && cand == (1 * kNumShears + kShearMax)) break;      // the fallback candidate itself failed
         }
     }
     int nchunks_final = want_prog ? sh_nchunks : -1;
@@ -399,7 +519,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         m.prog_steps = nchunks_final ? sh_total_steps : 0;
         m.flags = flags;
         m.prog_segs = nchunks_final ? sh_nsegs : 0;
-        m.reserved = 0;
+        m.prog_group_w = (int16_t)(nchunks_final ? prog_G : 0);
+        m.prog_shear = (int16_t)(nchunks_final ? prog_k : 0);
         m.sy = (double)sy;
         m.sx = (double)sx;
         m.syy = (double)syy;

@@ -81,7 +81,9 @@ def compact_taps(psfs, normalize, max_taps=1024):
     """Compact a batch of dense PSFs ([n, k, k] or [k, k] CUDA tensor, float32 / float16) into a TapSet.
 
     One launch for the batch, then one small device->host copy of the per-PSF summaries (counts, extents,
-    program sizes) that the blur launcher plans with.
+    program sizes) that the blur launcher plans with.  ``max_taps`` sizes the per-PSF tap list (what the exact-order
+    kernel walks); a PSF with more nonzero cells -- e.g. one widened by ``--dilate_psf`` (transforms.py:338-342) -- makes the
+    call repeat itself once with a list that holds the largest count, as the reference simply loops over more taps.
     """
     _require_cuda(psfs, "psfs")
     if psfs.dim() == 2:
@@ -100,9 +102,11 @@ def compact_taps(psfs, normalize, max_taps=1024):
                                              int(max_taps), _stream_ptr(psfs.device)))
         meta_bytes = buf[lay.meta_offset:lay.meta_offset + n * ctypes.sizeof(_lib.PsfMeta)].cpu().numpy().tobytes()
     meta = (_lib.PsfMeta * n).from_buffer_copy(meta_bytes)
-    for k in range(n):
-        if meta[k].flags & _lib.META_TRUNCATED:
-            raise _lib.DibError(_lib.ERR_CAPACITY, "PSF %d has %d taps, more than max_taps=%d" % (k, meta[k].count, max_taps))
+    worst = max(m.count for m in meta)
+    if worst > max_taps:
+        if worst > side * side:
+            raise _lib.DibError(_lib.ERR_CAPACITY, "PSF tap count %d exceeds the PSF's %d cells" % (worst, side * side))
+        return compact_taps(psfs, normalize, max_taps=1 << (worst - 1).bit_length())
     return TapSet(buf, lay, n, int(max_taps), side, meta)
 
 

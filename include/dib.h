@@ -68,7 +68,8 @@ typedef struct dib_psf_meta {
     int32_t prog_steps;       /* total weight vectors (window steps) of that program */
     int32_t flags;            /* DIB_META_* */
     int32_t prog_segs;        /* segments (column-group runs) of that program */
-    int32_t reserved;
+    int16_t prog_group_w;     /* PSF columns per group of that program (2 or 4; every step executes all of them) */
+    int16_t prog_shear;       /* columns per row the program's groups move: the tiled kernel's tiles are sheared alike */
     double sy, sx;            /* sums over the support of y, x         (transforms.py:367-371) */
     double syy, sxx, sxy;     /* sums of y*y, x*x, y*x over the support (transforms.py:373-376) */
 } dib_psf_meta;
