@@ -47,7 +47,7 @@ constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
 constexpr int kProducerRegs = DIB_PRODUCER_REGS;   // setmaxnreg budgets; together they must fit the 64K-register file
 // setmaxnreg moves registers inside the CTA's launch-time allocation (threads x the per-thread count the launch bound
 // allows, a multiple of 8); asking for more than the producers hand back blocks forever.
-constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8 > 255 ? 248 : (65536 / kThreads) / 8 * 8;
+constexpr int kLaunchRegs = (65536 / (kThreads * kCtasPerSm)) / 8 * 8 > 255 ? 248 : (65536 / (kThreads * kCtasPerSm)) / 8 * 8;
 constexpr int kComputeRegsRaw = (kThreads * kLaunchRegs - kProducerThreads * kProducerRegs) / (kComputeWarps * 32) / 8 * 8;
 constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
 static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
@@ -56,10 +56,10 @@ constexpr int kBoxesPerRow = kPitch / kBoxElems;
 constexpr int kRowBytes = kPitch * 4;
 constexpr int kTileBytes = kRowsMax * kRowBytes;
 constexpr int kStageBytes = kStageHdrBytes + kChunkAuxBytes + kTileBytes;
-constexpr int kSmemBytes = 2 * kStageBytes + kOutBufBytes + 128;    // + 6 mbarriers + 2 tile-ticket slots
-static_assert(kRowsMax * kBoxesPerRow <= kProducerThreads, "one TMA box per producer thread");
+constexpr int kSmemBytes = kStages * kStageBytes + kOutBufBytes + 128;    // + 3 * kStages mbarriers + 4 ticket / flag slots
+static_assert(kStages == 1 || kStages == 2, "one or two shared-memory stages");
 static_assert((kStageHdrBytes + kChunkAuxBytes) % 128 == 0 && kStageBytes % 128 == 0, "TMA destinations are 128-byte aligned");
-static_assert(kSmemBytes <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
+static_assert(kSmemBytes <= 232448 && kCtasPerSm * (kSmemBytes + 1024) <= 233472, "exceeds the shared memory of an sm_100 SM");
 
 struct alignas(64) TiledImage {
     CUtensorMap tmap;     // 1-D map over the image's elements, from the 16-byte-aligned address at or below src
@@ -113,6 +113,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware, do not spin
+}
+// Producer-group wait: ONE thread polls the mbarrier (with a back-off: nobody needs the answer within nanoseconds), the
+// other 127 block in a named barrier, which costs no issue slots -- four warps spinning on try_wait took ~14 % of the SM's
+// issue slots away from the compute warps (profiles/round2_notes.md).
+__device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity, int pt) {
+    if (pt == 0) {
+        uint32_t done = 0;
+        while (true) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+            if (done) break;
+            __nanosleep(96);
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(4 * 32) : "memory");
 }
 // non-blocking probe of a phase
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -300,11 +319,13 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
     const uint32_t aux = sbase + kStageHdrBytes, tile = aux + kChunkAuxBytes;
     const uint32_t aux_bytes = (uint32_t)(kChunkSegBytes + 4 * st.rec.group_w * (st.rec.wsteps + 1) + 15) & ~15u;
-    const int row = pt / kBoxesPerRow, box = pt - row * kBoxesPerRow;
-    const int irow = g.rt + row;
-    if (row < g.nrows && irow >= 0 && irow < im.H) {
-        const int64_t e = (int64_t)im.src_off + (int64_t)st.ch * im.src_cp + (int64_t)irow * im.src_rp + g.cl;
-        tma_box_1d(tile + (uint32_t)row * kRowBytes + (uint32_t)box * (kBoxElems * 4), &im.tmap, (int)(e & ~int64_t(3)) + box * kBoxElems, landed);
+    for (int t = pt; t < g.nrows * kBoxesPerRow; t += kProducerThreads) {
+        const int row = t / kBoxesPerRow, box = t - row * kBoxesPerRow;
+        const int irow = g.rt + row;
+        if (irow >= 0 && irow < im.H) {
+            const int64_t e = (int64_t)im.src_off + (int64_t)st.ch * im.src_cp + (int64_t)irow * im.src_rp + g.cl;
+            tma_box_1d(tile + (uint32_t)row * kRowBytes + (uint32_t)box * (kBoxElems * 4), &im.tmap, (int)(e & ~int64_t(3)) + box * kBoxElems, landed);
+        }
     }
     if (pt == kProducerThreads - 1)
         tma_bulk_g2s(aux, p.prog + (size_t)im.psf_index * kProgBytes + (size_t)st.rec.data_off16 * 16, aux_bytes, landed);
@@ -323,7 +344,7 @@ __device__ __forceinline__ void finish_stage(const TiledParams& p, const Stage& 
                                              uint64_t* full, int pt) {
     const TiledImage& im = p.img[st.img];
     const StageGeom g = stage_geom(im, st);
-    mbar_wait(landed, parity);
+    producer_wait(landed, parity, pt);
     const int top = min(g.nrows, max(0, -g.rt));                              // staged rows above the image
     const int bot = min(g.nrows - top, max(0, g.rt + g.nrows - im.H));         // staged rows below it
     if (top > 0 || bot > 0 || g.cl < 0 || g.cr >= im.W) {
@@ -423,15 +444,15 @@ template <int G>
 struct WeightVec {
     float v[G];
 };
+// Volatile loads: the vector fetched during step s is the one step s + 1 consumes, and ptxas must not sink the fetch below
+// the loop's exit branch into the step that needs it (it did: ~30 cycles of exposed shared-memory latency per step).
 template <int G>
 __device__ __forceinline__ WeightVec<G> lds_weights(uint32_t addr) {
     WeightVec<G> w;
     if constexpr (G == 2) {
-        const float2 t = lds_v2(addr);
-        w.v[0] = t.x; w.v[1] = t.y;
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(w.v[0]), "=f"(w.v[1]) : "r"(addr));
     } else {
-        const float4 t = lds_v4(addr);
-        w.v[0] = t.x; w.v[1] = t.y; w.v[2] = t.z; w.v[3] = t.w;
+        asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.v[0]), "=f"(w.v[1]), "=f"(w.v[2]), "=f"(w.v[3]) : "r"(addr));
     }
     return w;
 }
@@ -443,28 +464,30 @@ __device__ __forceinline__ WeightVec<G> lds_weights(uint32_t addr) {
 template <int G, int U>
 __device__ __forceinline__ bool sweep_step(float2 (&acc)[kR][kCC], float2 (&win)[kR][kCC + G - 1], uint32_t (&addr)[4], uint32_t stride4,
                                            int& s, int nsteps, uint32_t& wp, WeightVec<G> (&wv)[2]) {
-    load_row<kCC + G - 1, (kRows - U) % kRows>(win, addr[U & 3]);
+    load_row<kCC + G - 1, (kRows - U % kRows) % kRows>(win, addr[U & 3]);
     addr[U & 3] -= stride4;
     wp += 4u * G;
     wv[(U + 1) & 1] = lds_weights<G>(wp);                                 // weights of step s + 1 (zero vector past the end)
-    PairLoop<G, U, kR - 1>::run(acc, win, wv[U & 1].v);
+    PairLoop<G, U % kRows, kR - 1>::run(acc, win, wv[U & 1].v);
     ++s;
     return s < nsteps;
 }
 
-// kRows consecutive steps = one full rotation of the window registers
+// The unrolled body: kPeriod consecutive steps = whole rotations of the window registers (period kRows) AND of the row
+// skew (period 4), so both the window slot and the address register of a step are compile-time choices.
+constexpr int kPeriod = (kRows % 4 == 0) ? kRows : (kRows % 2 == 0 ? 2 * kRows : 4 * kRows);
 template <int G, int U>
 struct SweepRound {
     __device__ __forceinline__ static bool run(float2 (&acc)[kR][kCC], float2 (&win)[kR][kCC + G - 1], uint32_t (&addr)[4], uint32_t stride4,
                                                int& s, int nsteps, uint32_t& wp, WeightVec<G> (&wv)[2]) {
         if (!sweep_step<G, U>(acc, win, addr, stride4, s, nsteps, wp, wv)) return false;
-        if constexpr (U + 1 < kRows)
+        if constexpr (U + 1 < kPeriod)
             return SweepRound<G, U + 1>::run(acc, win, addr, stride4, s, nsteps, wp, wv);
         else
             return true;
     }
 };
-static_assert(kRows % 4 == 0, "the skew period (4 rows) must divide the window's rotation period");
+static_assert(kPeriod % 4 == 0 && kPeriod % kRows == 0 && kPeriod % 2 == 0, "period covers skew, window and weight-register rotation");
 
 // rows 1 .. kRows-1 of step 0's window (row 0 is step 0's own new row): logical row q -> slot q, staged row sr0 + q
 template <int W, int Q>
@@ -486,7 +509,7 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
     const int o1 = shear < 0 ? -(kRows - 1) * shear : 0;
     // The two compute warps that share an SM sub-partition (warp ids w and w + 4) walk the segments in opposite
     // orders: otherwise they run the same instruction sequence in lockstep and their load phases coincide.
-    const bool reverse = ((threadIdx.x >> 5) & 4) != 0;
+    const bool reverse = (((threadIdx.x >> 5) - kProducerWarps) & 4) != 0 || (kComputeWarps == 4 && 2 * blockIdx.x >= gridDim.x);
 #pragma unroll 1
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int sg = reverse ? nseg - 1 - sgi : sgi;
@@ -697,15 +720,15 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
 // ---------------------------------------------------------------- kernel
 // kEpi selects the epilogue variant (kEpiNone / kEpiAffine / kEpiGeneral); batches without one run the leanest.
 template <int kEpi>
-__global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
-    float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
-    uint64_t* full = bars;          // [2] producers -> consumers: stage loaded and patched
-    uint64_t* empty = bars + 2;     // [2] consumers -> producers: stage may be refilled
-    uint64_t* landed = bars + 4;    // [2] TMA -> producers: the stage's boxes have arrived, borders may be patched
-    int* tile_slots = reinterpret_cast<int*>(bars + 6);
+    float* obuf_all = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kOutBufBytes);
+    uint64_t* full = bars;                  // [kStages] producers -> consumers: stage loaded and patched
+    uint64_t* empty = bars + kStages;       // [kStages] consumers -> producers: stage may be refilled
+    uint64_t* landed = bars + 2 * kStages;  // [kStages] TMA -> producers: the stage's boxes have arrived, borders may be patched
+    int* tile_slots = reinterpret_cast<int*>(bars + 3 * kStages);
     const int warp = threadIdx.x >> 5;
 
     // Programmatic dependent launch: let the next launch on the stream start filling SMs as this grid's CTAs retire, and
@@ -715,22 +738,24 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], kProducerThreads);      // one cp.async-arrive per producer thread
-        mbar_init(&full[1], kProducerThreads);
-        mbar_init(&landed[0], 1);                   // one arrive.expect_tx; the boxes complete the transaction bytes
-        mbar_init(&landed[1], 1);
-        mbar_init(&empty[0], kComputeWarps);
-        mbar_init(&empty[1], kComputeWarps);
+        for (int b = 0; b < kStages; ++b) {
+            mbar_init(&full[b], kProducerThreads);      // one cp.async-arrive per producer thread
+            mbar_init(&landed[b], 1);                   // one arrive.expect_tx; the boxes complete the transaction bytes
+            mbar_init(&empty[b], kComputeWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // Register budget: the launch splits the register file evenly over all warps; the producer warpgroup hands most of
     // its share back so that the compute warps can hold kR * kCC accumulators + kR * (kCC + 3) window values per thread.
-    if (warp >= kComputeWarps) {
+    // The producers are the LOWEST warp ids: the issue arbiter favours high warp ids, and producer warps only ever wait,
+    // issue a copy or patch a border.
+    // Stage n lives in buffer n % kStages; the k-th use of a buffer completes phase k of its barriers (parity k & 1).
+    if (warp < kProducerWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         // ------------------------------------------------ producer warpgroup
-        const int pt = threadIdx.x - kComputeWarps * 32;
+        const int pt = threadIdx.x;
         Stage cur, nxt;
         int nfetch = 0;
         cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
@@ -740,13 +765,14 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             cur.rec = load_chunk_rec(p, cur.img, 0);
             issue_stage(p, cur, stage_base(smem_base, 0), &landed[0], pt);
         }
-        // stage n lives in buffer n & 1.  Per iteration: look up stage n + 1; if its buffer is already free start its loads
-        // right away (memory-bound regime: two stages in flight), patch and publish stage n, else start them afterwards.
+        // Per iteration: look up stage n + 1; with two buffers, if the other one is already free start its loads right away
+        // (memory-bound regime: two stages in flight); patch and publish stage n; else start the loads of n + 1 once the
+        // consumers have released its buffer.
         for (int n = 0;; ++n) {
-            const int b = n & 1, b1 = b ^ 1;
+            const int b = n % kStages, b1 = (n + 1) % kStages;
             if (cur.tile < 0) {
                 // no more work: publish a stop marker in the buffer stage n would have used
-                if (n >= 2) mbar_wait(&empty[b], (uint32_t)(((n >> 1) - 1) & 1));
+                if (n >= kStages) producer_wait(&empty[b], (uint32_t)((n / kStages - 1) & 1), pt);
                 if (pt == 0) reinterpret_cast<StageHdr*>(smem + (size_t)b * kStageBytes)->tile = -1;
                 __threadfence_block();
                 cp_async_mbar_arrive(&full[b]);
@@ -762,15 +788,21 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
                 break;
             }
             next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the work below
-            const uint32_t empty_parity = (uint32_t)((((n + 1) >> 1) - 1) & 1);
+            const uint32_t empty_parity = (uint32_t)(((n + 1) / kStages - 1) & 1);
             bool issued = false;
-            if (nxt.tile >= 0 && (n + 1 < 2 || __all_sync(0xffffffffu, mbar_test(&empty[b1], empty_parity)))) {     // warp-uniform
-                issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
-                issued = true;
+            if (kStages > 1 && nxt.tile >= 0) {
+                // thread 0 probes the buffer of stage n + 1 and shares the answer (the flag slot alternates with n)
+                int* flag = tile_slots + 2 + (n & 1);
+                if (pt == 0) *flag = (n + 1 < kStages || mbar_test(&empty[b1], empty_parity)) ? 1 : 0;
+                asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+                if (*flag) {
+                    issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
+                    issued = true;
+                }
             }
-            finish_stage(p, cur, stage_base(smem_base, b), &landed[b], (uint32_t)((n >> 1) & 1), &full[b], pt);
+            finish_stage(p, cur, stage_base(smem_base, b), &landed[b], (uint32_t)((n / kStages) & 1), &full[b], pt);
             if (nxt.tile >= 0 && !issued) {
-                mbar_wait(&empty[b1], empty_parity);
+                if (n + 1 >= kStages) producer_wait(&empty[b1], empty_parity, pt);
                 issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
             }
             cur = nxt;
@@ -778,13 +810,14 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
         // ------------------------------------------------ compute warps
-        const int wrow = warp / kWarpCols, wcol = warp % kWarpCols;
+        const int cw = warp - kProducerWarps;
+        const int wrow = cw / kWarpCols, wcol = cw % kWarpCols;
         float2 acc[kR][kCC];
-        const uint32_t obuf = smem_u32(obuf_all + warp * 2 * kOutPitch);
+        const uint32_t obuf = smem_u32(obuf_all + cw * 2 * kOutPitch);
         for (int n = 0;; ++n) {
-            const int b = n & 1;
+            const int b = n % kStages;
             const uint32_t sbase = stage_base(smem_base, b);
-            mbar_wait(&full[b], (n >> 1) & 1);
+            mbar_wait(&full[b], (n / kStages) & 1);
             StageHdr h;
             {   // explicit vector loads keep the header in registers
                 const int4* hp = reinterpret_cast<const int4*>(smem + (size_t)b * kStageBytes);
@@ -934,8 +967,9 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     // Overlapped launches share SMs only while the earlier grid drains: with one CTA per SM and a full grid at most two
     // launches are ever co-resident, which the four scheduler slots cover.  A grid smaller than the machine could be
     // co-resident with many successors, so it always orders itself after its predecessor.
-    p.overlap_prev = (overlap_prev && total >= sm_count) ? 1 : 0;
-    const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
+    const int max_ctas = sm_count * kCtasPerSm;
+    p.overlap_prev = (overlap_prev && total >= max_ctas) ? 1 : 0;
+    const int grid = total < max_ctas ? total : max_ctas;     // persistent: kCtasPerSm CTAs per SM
     // launched with the programmatic-stream-serialization attribute: the kernel itself decides (griddepcontrol.wait)
     // whether it orders itself after the previous launch
     cudaLaunchConfig_t cfg = {};

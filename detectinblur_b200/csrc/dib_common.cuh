@@ -41,6 +41,12 @@ void set_error(const char* fmt, ...);
 #ifndef DIB_WARP_COLS
 #define DIB_WARP_COLS 2
 #endif
+#ifndef DIB_STAGES
+#define DIB_STAGES 2
+#endif
+#ifndef DIB_CTAS_PER_SM
+#define DIB_CTAS_PER_SM 1
+#endif
 constexpr int kR = DIB_R;                   // row pairs per thread (rows r and r + kR share 64-bit accumulators: FFMA2)
 constexpr int kRows = 2 * kR;               // output rows per thread = rotation period of the register window
 constexpr int kCC = 7;                      // output columns per thread (odd lane stride: conflict-free scalar LDS)
@@ -60,12 +66,17 @@ constexpr int kStageHdrBytes = 64;
 // has none -- so the sweep has no data-dependent branches.  Segments are packed into CHUNKS (a band of neighbouring groups
 // x a window of rows) whose true tap extents fit one shared-memory stage: rows <= kChunkTapRows, columns <= kPitch - kTW
 // minus what the shear costs.
-constexpr int kChunkAuxBytes = 2240;        // segment records + weight vectors of one chunk (stage header + aux = 18 * 128 B)
+constexpr int kChunkTapRowsCap = 36;        // most PSF rows a chunk may span, whatever the stage could hold
+constexpr int kChunkAuxBytes = 3776;        // segment records + weight vectors of one chunk (stage header + aux = 30 * 128 B)
 constexpr int kStageBytesFor(int rows) { return kStageHdrBytes + kChunkAuxBytes + rows * kPitch * 4; }
-constexpr int kSmemBudget = 232448 - 128;   // 227 KB per CTA minus barriers / ticket slots
+constexpr int kStages = DIB_STAGES;         // shared-memory stages per CTA (1: the CTAs co-resident on an SM alternate instead)
+constexpr int kCtasPerSm = DIB_CTAS_PER_SM;
+// 228 KB of shared memory per SM, 1 KB of which the system reserves per resident CTA; at most 227 KB per CTA
+constexpr int kSmemBudget = (233472 / kCtasPerSm - 1024 < 232448 ? 233472 / kCtasPerSm - 1024 : 232448) - 128;   // minus barriers / ticket slots
 constexpr int kOutBufBytes = kComputeWarps * 2 * kOutPitch * 4;
-constexpr int kRowsMax = (kSmemBudget - kOutBufBytes - 2 * (kStageHdrBytes + kChunkAuxBytes)) / (2 * kPitch * 4);   // staged rows
-constexpr int kChunkTapRows = kRowsMax - kTH + 1;      // PSF rows one chunk may span (dy_hi - dy_lo + 1)
+constexpr int kRowsMaxRaw = (kSmemBudget - kOutBufBytes - kStages * (kStageHdrBytes + kChunkAuxBytes)) / (kStages * kPitch * 4);
+constexpr int kRowsMax = kRowsMaxRaw > 60 ? 60 : kRowsMaxRaw;   // staged rows (one TMA box per producer thread and row half)
+constexpr int kChunkTapRows = kRowsMax - kTH + 1 < kChunkTapRowsCap ? kRowsMax - kTH + 1 : kChunkTapRowsCap;   // PSF rows per chunk
 static_assert(kChunkTapRows >= 8, "tile too tall for the shared-memory stage");
 constexpr int kShearMax = (kRows <= 6) ? 2 : 1;       // |shear|: (kRows - 1) * |shear| extra columns per tile row band
 constexpr int kChunkSegSlots = 12;          // segments (groups) per chunk

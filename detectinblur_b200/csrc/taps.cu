@@ -375,10 +375,17 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                             for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
                         int cursor = ymin, nbc = 0;
                         const int base = pass ? sh_band_base[tid] : 0;
+                        // rows of the band are cut into windows of equal height (not kChunkTapRows, kChunkTapRows, ...,
+                        // remainder): chunks of similar length hide each other's staging
+                        int bf, bl;
+                        mask_range_first_last(band, ymin, ymax, bf, bl);
+                        const int bspan = bf < 0 ? 1 : bl - bf + 1;
+                        const int nwin = (bspan + kChunkTapRows - 1) / kChunkTapRows;
+                        const int win_rows = (bspan + nwin - 1) / nwin;
                         while (true) {
                             const int y0 = mask_first_from(band, cursor);
                             if (y0 < 0) break;
-                            const int y1 = min(y0 + kChunkTapRows - 1, ymax);
+                            const int y1 = min(y0 + win_rows - 1, ymax);
                             if (pass) {
                                 ChunkRec c;
                                 int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);

@@ -74,3 +74,56 @@ if __name__ == "__main__":
             print("R%d kmax%d %s: eff %.3f reuse %.2f  fma-cycles/ideal %.2f  cost/ideal %.2f smem@fma-bound %.0f%% chunks %d | %s" % (
                 R, kmax, name, tot["taps"] / tot["slots"], tot["taps"] * R * C / tot["loads"], 2 * tot["ffma2"] / ideal,
                 tot["cost"] / ideal, 100 * 4 * tot["loads"] / (2 * tot["ffma2"]), tot["chunks"], " ".join(desc)))
+
+
+def plan_dp(psf, k, R=8, chunk_rows=21, widths=(1, 2), allow4=False):
+    """Optimal partition of the sheared columns into groups of the given widths (dynamic programming over columns),
+    cost per group = span * step_cost(G) + ceil(span / chunk_rows) * fill_cost(G)."""
+    ys, xs = np.nonzero(psf)
+    ymin = ys.min()
+    xp = xs - k * (ys - ymin)
+    x0, x1 = xp.min(), xp.max()
+    n = x1 - x0 + 1
+    first = np.full(n, 10**6)
+    last = np.full(n, -1)
+    for y, x in zip(ys, xp - x0):
+        first[x] = min(first[x], y)
+        last[x] = max(last[x], y)
+    kR = R // 2
+
+    def step_cost(G):
+        return max(2 * G * kR * C, 4 * (C + G)) + 4
+
+    def fill_cost(G):
+        return 4 * (R - 1) * (C + G - 1) + 60
+
+    INF = 10**12
+    best = [INF] * (n + 1)
+    choice = [0] * (n + 1)
+    best[0] = 0
+    for i in range(n):
+        if best[i] >= INF:
+            continue
+        for G in widths + ((4,) if allow4 else ()):
+            j = min(n, i + G)
+            f = first[i:j].min()
+            l = last[i:j].max()
+            if l < 0:
+                c = 0
+            else:
+                span = l - f + 1
+                c = span * step_cost(G) + -(-span // chunk_rows) * fill_cost(G)
+            if best[i] + c < best[j]:
+                best[j] = best[i] + c
+                choice[j] = (i, G, 0 if l < 0 else l - f + 1)
+    # walk back
+    j = n
+    slots = steps = segs = 0
+    while j > 0:
+        i, G, span = choice[j]
+        if span:
+            slots += span * G
+            steps += span
+            segs += 1
+        j = i
+    return dict(cost=best[n], slots=slots, steps=steps, segs=segs, eff=len(ys) / slots)
