@@ -39,7 +39,7 @@
 namespace dib {
 
 #ifndef DIB_PRODUCER_REGS
-#define DIB_PRODUCER_REGS 56
+#define DIB_PRODUCER_REGS 88
 #endif
 constexpr int kProducerWarps = 4;           // one warpgroup: a thread issues at most one TMA box per stage
 constexpr int kProducerThreads = kProducerWarps * 32;
@@ -90,6 +90,31 @@ struct TiledParams {
     SchedWords* sched;            // dynamic tile scheduler (tap set buffer): tiles are handed out in index order
     int overlap_prev;             // DIB_ALGO_OVERLAP: do not wait for the grid launched before this one
 };
+
+// ---------------------------------------------------------------- optional timeline trace (kernel experiments only)
+#ifdef DIB_TRACE
+constexpr int kTracePerWarp = 4096;
+__device__ unsigned long long g_trace[16 * kTracePerWarp];
+__device__ unsigned int g_trace_n[16];
+__device__ __forceinline__ void trace_event(int ev, int arg) {
+    // per-warp slices, the write position kept in shared memory (no global atomics: their round trip would dominate)
+    __shared__ unsigned int pos[16];
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        unsigned int i = pos[w];
+        if (i >= (unsigned)kTracePerWarp) i = 0;         // shared memory starts uninitialised; slices are reset by the host
+        i = (ev == 63) ? 0 : i;
+        if (i < (unsigned)kTracePerWarp - 1) {
+            g_trace[w * kTracePerWarp + i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(arg & 0xfff) << 12) | (w << 6) | (unsigned)ev;
+            pos[w] = i + 1;
+            g_trace_n[w] = i + 1;
+        }
+    }
+}
+#define DIB_TRACE_EVENT(ev, arg) trace_event(ev, arg)
+#else
+#define DIB_TRACE_EVENT(ev, arg)
+#endif
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -335,48 +360,78 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
 }
 
-// Producer group, second half of a stage: once the boxes have landed, write what they could not deliver -- every pixel of
-// the staged rows above / below the image and, in the other rows, the columns left of the image's first and right of its
-// last pixel: reflect-101 pixels (4-byte cp.async from the mirrored source) or zeros -- each at the float offset the skew
-// progression assigns to its row, and hand the stage to the consumers: every producer thread arrives on "full" when its
-// own patches have landed.
+// Producer group, second half of a stage: once the boxes have landed, write what they could not deliver and hand the
+// stage to the consumers.  Two passes, a warp per staged row, a lane per column:
+//   1. rows inside the image: the columns left of the image's first and right of its last pixel are reflect-101 pixels of
+//      the SAME row, which is already in shared memory -- one LDS + STS each (a mirrored column that the stage does not
+//      hold -- only a last column tile a few pixels wide -- comes from global memory with a 4-byte cp.async);
+//   2. rows above / below the image: reflect-101 copies of staged rows inside it, border columns included, shifted by the
+//      difference of the two rows' skews.
+// Zero-padding mode stores zeros instead.  Every producer thread then arrives on "full" (once its cp.asyncs, if any,
+// have landed).
 __device__ __forceinline__ void finish_stage(const TiledParams& p, const Stage& st, uint32_t sbase, uint64_t* landed, uint32_t parity,
                                              uint64_t* full, int pt) {
     const TiledImage& im = p.img[st.img];
     const StageGeom g = stage_geom(im, st);
+    DIB_TRACE_EVENT(10, st.chunk);
     producer_wait(landed, parity, pt);
+    DIB_TRACE_EVENT(11, st.chunk);
     const int top = min(g.nrows, max(0, -g.rt));                              // staged rows above the image
     const int bot = min(g.nrows - top, max(0, g.rt + g.nrows - im.H));         // staged rows below it
-    if (top > 0 || bot > 0 || g.cl < 0 || g.cr >= im.W) {
+    const bool cols_out = g.cl < 0 || g.cr >= im.W;
+    if (top > 0 || bot > 0 || cols_out) {
         const uint32_t tile = sbase + kStageHdrBytes + kChunkAuxBytes;
         const float* plane = static_cast<const float*>(im.src) + (int64_t)st.ch * im.src_cp;
+        const int lane = pt & 31, pw = pt >> 5;
         const int ncols = g.cr - g.cl + 1;
-        const int xa = max(g.cl, 0), xb1 = min(g.cr, im.W - 1) + 1;          // in-image columns [xa, xb1)
-        const int nleft = xa - g.cl, nborder = nleft + g.cr + 1 - xb1;
-        const int n_out = (top + bot) * ncols;
-        const int total = n_out + (g.nrows - top - bot) * nborder;
-        for (int idx = pt; idx < total; idx += kProducerThreads) {
-            int r2, col;
-            if (idx < n_out) {                       // a row outside the image: all of its columns
-                const int q = idx / ncols;
-                r2 = q < top ? q : g.nrows - bot + (q - top);
-                col = g.cl + (idx - q * ncols);
-            } else {                                 // a row inside the image: its border columns
-                const int k2 = idx - n_out, q = k2 / nborder, k = k2 - q * nborder;
-                r2 = top + q;
-                col = k < nleft ? g.cl + k : xb1 + (k - nleft);
+        if (cols_out) {
+            const int xa = max(g.cl, 0), xb1 = min(g.cr, im.W - 1) + 1;          // in-image columns [xa, xb1)
+            const int nleft = xa - g.cl, nborder = nleft + g.cr + 1 - xb1;
+            for (int r2 = top + pw; r2 < g.nrows - bot; r2 += kProducerWarps) {
+                const int skew = (g.skew0 + r2 * g.dskew) & 3;
+                const uint32_t row = tile + (uint32_t)r2 * kRowBytes + 4u * (uint32_t)(skew - g.cl);     // + 4 * col
+                for (int k = lane; k < nborder; k += 32) {
+                    const int col = k < nleft ? g.cl + k : xb1 + (k - nleft);
+                    if (im.zero_pad) {
+                        sts_f32(row + 4u * (uint32_t)col, 0.0f);
+                    } else {
+                        const int sc = reflect101(col, im.W);
+                        if (sc >= g.cl && sc - g.cl + skew < kPitch)
+                            sts_f32(row + 4u * (uint32_t)col, lds_f32(row + 4u * (uint32_t)sc));
+                        else
+                            cp_async_4(row + 4u * (uint32_t)col, plane + (int64_t)(g.rt + r2) * im.src_rp + sc);
+                    }
+                }
             }
-            const int irow = g.rt + r2;
-            const int skew = (g.skew0 + r2 * g.dskew) & 3;
-            const uint32_t d = tile + (uint32_t)r2 * kRowBytes + 4u * (uint32_t)(col - g.cl + skew);
-            if (im.zero_pad)
-                sts_f32(d, 0.0f);
-            else
-                cp_async_4(d, plane + (int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W));
+        }
+        if (top > 0 || bot > 0) {
+            // pass 2 reads what pass 1 wrote (and, through the fallback, what its cp.asyncs deliver)
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+            for (int q = pw; q < top + bot; q += kProducerWarps) {
+                const int r2 = q < top ? q : g.nrows - bot + (q - top);
+                const int irow = g.rt + r2;
+                const int skew = (g.skew0 + r2 * g.dskew) & 3;
+                const uint32_t drow = tile + (uint32_t)r2 * kRowBytes + 4u * (uint32_t)skew;              // + 4 * (col - cl)
+                if (im.zero_pad) {
+                    for (int k = lane; k < ncols; k += 32) sts_f32(drow + 4u * (uint32_t)k, 0.0f);
+                    continue;
+                }
+                const int srow_img = reflect101(irow, im.H);
+                const int rs = srow_img - g.rt;                                  // staged row that holds the mirrored image row
+                if (rs >= 0 && rs < g.nrows) {
+                    const uint32_t srow = tile + (uint32_t)rs * kRowBytes + 4u * (uint32_t)((g.skew0 + rs * g.dskew) & 3);
+                    for (int k = lane; k < ncols; k += 32) sts_f32(drow + 4u * (uint32_t)k, lds_f32(srow + 4u * (uint32_t)k));
+                } else {
+                    for (int k = lane; k < ncols; k += 32)
+                        cp_async_4(drow + 4u * (uint32_t)k, plane + (int64_t)srow_img * im.src_rp + reflect101(g.cl + k, im.W));
+                }
+            }
         }
     }
-    __threadfence_block();      // zero fills are plain stores: order them before the arrive that publishes the stage
+    __threadfence_block();      // the patches are plain stores: order them before the arrive that publishes the stage
     cp_async_mbar_arrive(full);
+    DIB_TRACE_EVENT(12, st.chunk);
 }
 
 // ---------------------------------------------------------------- compute
@@ -519,6 +574,7 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
         const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (G - 1) + o1 + dx_hi;
         const int sr0 = wrow * kRows - seg_dy0 + dy_hi;    // staged row of output row 0 at step 0
+        DIB_TRACE_EVENT(2, nsteps);
         const uint32_t a0 = tile + 4u * (uint32_t)(sr0 * kPitch + colbase);
         const int skew_sr0 = skew0 + sr0 * dskew;           // (.. & 3) = skew of staged row sr0
         uint32_t wp = aux + kChunkSegBytes + 4u * G * (uint32_t)seg_woff;
@@ -533,8 +589,10 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         for (int j = 0; j < 4; ++j) addr[j] = a0 - (uint32_t)j * stride + 4u * (uint32_t)((skew_sr0 - j * dskew) & 3);
         int s = 0;
 #pragma unroll 1
+        DIB_TRACE_EVENT(6, sg);
         while (SweepRound<G, 0>::run(acc, win, addr, 4u * stride, s, nsteps, wp, wv)) {
         }
+        DIB_TRACE_EVENT(3, sg);
     }
 }
 
@@ -736,6 +794,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const 
     // (and flush) before touching global memory.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
+    DIB_TRACE_EVENT(63, 0);
 
     if (threadIdx.x == 0) {
         for (int b = 0; b < kStages; ++b) {
@@ -802,8 +861,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const 
             }
             finish_stage(p, cur, stage_base(smem_base, b), &landed[b], (uint32_t)((n / kStages) & 1), &full[b], pt);
             if (nxt.tile >= 0 && !issued) {
+                DIB_TRACE_EVENT(13, n);
                 if (n + 1 >= kStages) producer_wait(&empty[b1], empty_parity, pt);
+                DIB_TRACE_EVENT(14, n);
                 issue_stage(p, nxt, stage_base(smem_base, b1), &landed[b1], pt);
+                DIB_TRACE_EVENT(15, n);
             }
             cur = nxt;
         }
@@ -817,7 +879,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const 
         for (int n = 0;; ++n) {
             const int b = n % kStages;
             const uint32_t sbase = stage_base(smem_base, b);
+            DIB_TRACE_EVENT(0, n);
             mbar_wait(&full[b], (n / kStages) & 1);
+            DIB_TRACE_EVENT(1, n);
             StageHdr h;
             {   // explicit vector loads keep the header in registers
                 const int4* hp = reinterpret_cast<const int4*>(smem + (size_t)b * kStageBytes);
@@ -846,8 +910,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const 
                     compute_chunk<4>(acc, sbase, h.nseg, h.dy_hi, h.dx_hi, h.shear, h.skew0, h.dskew, wrow, wcol);
             }
             __syncwarp();
+            DIB_TRACE_EVENT(4, n);
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
             if (h.last_chunk && active) store_rows<kEpi>(p, im, h.ch, row0, col0, h.shear, acc, obuf);
+            DIB_TRACE_EVENT(5, n);
         }
     }
 }
@@ -994,3 +1060,21 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
 }
 
 }  // namespace dib
+
+#ifdef DIB_TRACE
+// kernel experiments: copy out (and reset) the timeline recorded by CTA 0 of the launches since the last call
+extern "C" __attribute__((visibility("default"))) int dib_debug_trace(unsigned long long* out, int max_events) {
+    unsigned int n[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, dib::g_trace_n, sizeof(n));
+    int total = 0;
+    for (int w = 0; w < 16; ++w) {
+        int c = (int)n[w];
+        if (c > dib::kTracePerWarp) c = dib::kTracePerWarp;
+        if (total + c > max_events) c = max_events - total;
+        if (c > 0) cudaMemcpyFromSymbol(out + total, dib::g_trace, sizeof(unsigned long long) * c, sizeof(unsigned long long) * w * dib::kTracePerWarp);
+        total += c > 0 ? c : 0;
+    }
+    return total;
+}
+#endif
