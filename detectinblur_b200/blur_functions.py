@@ -108,7 +108,8 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     exact = _exact_default() if exact is None else exact
     if n == 0:
         return BlurPlan((_lib.Image * 1)(), 0, tapset, torch.float32, _lib.ALGO_AUTO, 0, torch.device("cuda"), [], [])
-    if images[0].dtype == torch.float16 and not exact:
+    if images[0].dtype == torch.float16 and not exact and not _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd,
+                                                                             clamp, philox_seed, gamma, pad_mode):
         return _HalfPlan(images, tapset, psf_indices, outs, noise, noise_sd, clamp, philox_seed, mean, std, gamma, pad_mode)
     dev = images[0].device
     dtype = images[0].dtype
@@ -193,8 +194,8 @@ def _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd, clamp, ph
         if img.shape[1] <= 64 or img.shape[2] <= 64 or tapset is None or tapset.side > 129:
             return False
         m = tapset.meta[int(psf_indices[k])]
-        if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM):
-            return False
+        if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM) or m.prog_group_w != 0:
+            return False                                   # in-kernel half I/O is the masked kernel's (small PSFs)
         if outs is not None and outs[k] is not None:
             o = outs[k]
             if o.dtype != torch.float16 or o.dim() != 3 or o.data_ptr() % 16 or o.stride(1) % 8 or (o.shape[0] > 1 and o.stride(0) % 8):

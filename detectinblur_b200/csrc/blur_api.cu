@@ -8,20 +8,37 @@
 namespace dib {
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
                    int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
+// dense sheared program (blur_tiled.cu): large PSFs, float32 images
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
                  SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st);
+namespace mk {
+// masked program (blur_masked.cu): PSFs whose support fits one chunk, float32 and float16 images
+int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st);
+}  // namespace mk
 
-static bool tiled_eligible(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
-    if (meta_host == nullptr || im.psf_index < 0) return false;
-    // float32 images only: half images go through the wrapper's casts (fp32 accumulation, one rounding) or, for the
-    // reference's bits, the exact-order kernel
-    if (io_dtype != DIB_F32) return false;
+enum { kNotTiled = 0, kMasked = 1, kDense = 2 };
+
+// which tiled kernel, if any, takes this image
+static int tiled_kind(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
+    if (meta_host == nullptr || im.psf_index < 0) return kNotTiled;
     // reflect-101 or zero padding about centre 63; tiny images (the reference's own zero-padding case) stay on the generic kernel
-    if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return false;
+    if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return kNotTiled;
     const dib_psf_meta& m = meta_host[im.psf_index];
-    if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return false;
-    if (io_dtype == DIB_F32 && ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u)) return false;
-    return true;
+    if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return kNotTiled;
+    const int kind = m.prog_group_w == 0 ? kMasked : kDense;
+    if (io_dtype == DIB_F16) {
+        // half I/O (masked kernel only): fp32 accumulation, rounded to half once (the reference's half loop rounds after every
+        // tap -- callers that need its bits pass DIB_ALGO_GENERIC).  Needs 16-byte-aligned destination rows and at most the
+        // normalize epilogue.  Half images with a large PSF go through the wrapper's casts around the float32 path.
+        if (kind != kMasked) return kNotTiled;
+        if ((reinterpret_cast<uintptr_t>(im.dst) & 15u) || (im.dst_row_pitch & 7) || (im.dst_chan_pitch & 7)) return kNotTiled;
+        if (reinterpret_cast<uintptr_t>(im.src) & 1u) return kNotTiled;
+        if (im.epilogue & ~DIB_EPI_NORMALIZE) return kNotTiled;
+    } else if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) {
+        return kNotTiled;
+    }
+    return kind;
 }
 }  // namespace dib
 
@@ -34,7 +51,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     DIB_CHECK_ARG(n_images >= 0 && n_images <= DIB_MAX_BATCH, "dib_blur_batch: n_images %d outside [0, %d]", n_images, DIB_MAX_BATCH);
     DIB_CHECK_ARG(io_dtype == DIB_F32 || io_dtype == DIB_F16, "dib_blur_batch: io_dtype must be DIB_F32 or DIB_F16");
     const bool overlap_prev = (algo & DIB_ALGO_OVERLAP) != 0;
-    const int sched_slot = (algo >> 12) & 3;
+    const int sched_slot = (algo >> 12) & (kSchedSlots - 1);
     DIB_CHECK_ARG((algo & ~(0xff | DIB_ALGO_OVERLAP | DIB_ALGO_SLOT(3))) == 0, "dib_blur_batch: unknown algo flags 0x%x", algo);
     algo &= 0xff;
     DIB_CHECK_ARG(algo == DIB_ALGO_AUTO || algo == DIB_ALGO_GENERIC || algo == DIB_ALGO_TILED, "dib_blur_batch: unknown algo %d", algo);
@@ -68,36 +85,48 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     SchedWords* sched = reinterpret_cast<SchedWords*>(base + L.sched_offset) + sched_slot;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    // split the batch: tiled kernel where eligible (heaviest PSFs first), exact-order kernel for the rest
-    int order[DIB_MAX_BATCH];
-    int n_sel = 0;
+    // split the batch: a tiled kernel where eligible (heaviest PSFs first), exact-order kernel for the rest
+    int order[2][DIB_MAX_BATCH];
+    int n_kind[2] = {0, 0};
     uint32_t tiled_mask = 0;
     if (algo != DIB_ALGO_GENERIC) {
         for (int k = 0; k < n_images; ++k) {
-            if (tiled_eligible(images[k], meta_host, io_dtype)) {
-                order[n_sel++] = k;
+            const int kind = tiled_kind(images[k], meta_host, io_dtype);
+            if (kind != kNotTiled) {
+                order[kind - 1][n_kind[kind - 1]++] = k;
                 tiled_mask |= 1u << k;
             } else if (algo == DIB_ALGO_TILED) {
-                set_error("dib_blur_batch: image %d is not eligible for the tiled kernel (reflect or zero mode, sides > 64, PSF with a "
-                          "tiled program and host meta; half images: 16-byte-aligned destination rows, normalize epilogue at most)", k);
+                set_error("dib_blur_batch: image %d is not eligible for a tiled kernel (reflect or zero mode, sides > 64, PSF with a "
+                          "tiled program and host meta; half images: a PSF within 18 x 20 cells, 16-byte-aligned destination rows, "
+                          "normalize epilogue at most)", k);
                 return DIB_ERR_UNSUPPORTED;
             }
         }
         // insertion sort by tap count, descending (stable): the dynamic scheduler hands out long tiles first
-        for (int a = 1; a < n_sel; ++a) {
-            const int v = order[a];
-            const int cv = meta_host[images[v].psf_index].count;
-            int b = a - 1;
-            while (b >= 0 && meta_host[images[order[b]].psf_index].count < cv) {
-                order[b + 1] = order[b];
-                --b;
+        for (int q = 0; q < 2; ++q) {
+            for (int a = 1; a < n_kind[q]; ++a) {
+                const int v = order[q][a];
+                const int cv = meta_host[images[v].psf_index].count;
+                int b = a - 1;
+                while (b >= 0 && meta_host[images[order[q][b]].psf_index].count < cv) {
+                    order[q][b + 1] = order[q][b];
+                    --b;
+                }
+                order[q][b + 1] = v;
             }
-            order[b + 1] = v;
         }
     }
+    const int n_sel = n_kind[0] + n_kind[1];
     int nl = 0;
-    if (n_sel > 0) {
-        const int rc = launch_tiled(images, order, n_sel, meta_host, prog, sched, philox_seed, philox_offset, io_dtype, overlap_prev, st);
+    if (n_kind[0] > 0) {
+        const int rc = mk::launch_tiled(images, order[0], n_kind[0], meta_host, prog, sched, philox_seed, philox_offset, io_dtype, overlap_prev, st);
+        if (rc != DIB_OK) return rc;
+        ++nl;
+    }
+    if (n_kind[1] > 0) {
+        // its own scheduler words: the two tiled launches of one call may be co-resident
+        const int rc = launch_tiled(images, order[1], n_kind[1], meta_host, prog, sched + kSchedSlots, philox_seed, philox_offset, io_dtype,
+                                    overlap_prev, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

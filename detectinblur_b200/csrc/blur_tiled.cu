@@ -588,8 +588,8 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
 #pragma unroll
         for (int j = 0; j < 4; ++j) addr[j] = a0 - (uint32_t)j * stride + 4u * (uint32_t)((skew_sr0 - j * dskew) & 3);
         int s = 0;
-#pragma unroll 1
         DIB_TRACE_EVENT(6, sg);
+#pragma unroll 1
         while (SweepRound<G, 0>::run(acc, win, addr, 4u * stride, s, nsteps, wp, wv)) {
         }
         DIB_TRACE_EVENT(3, sg);

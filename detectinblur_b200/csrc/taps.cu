@@ -10,7 +10,7 @@
 // One CTA per PSF, one launch per batch.  PSFs up to 129 x 129 are first staged in shared memory with independent
 // (unrolled) loads, so the three passes over the cells and the program builder pay one round of global latency
 // instead of one per loop iteration; larger canvases (the 256 branch) read global memory throughout.
-#include "dib_common.cuh"
+#include "masked_common.cuh"
 
 namespace dib {
 
@@ -76,7 +76,6 @@ __device__ inline int block_min_int(int v, int* sh) {
 
 constexpr int kMaxGroups = 192;       // sheared groups of one PSF (support width + shear drift, in groups of 2)
 constexpr int kMaxBands = 64;
-constexpr int kBandMaxChunks = 128 / kChunkTapRows + 2;
 constexpr int kNumShears = 2 * kShearMax + 1;
 constexpr int kNumCand = 2 * kNumShears;          // group width 2 or 4 x shear -kShearMax .. kShearMax
 
@@ -126,6 +125,172 @@ __device__ __forceinline__ float psf_cell(const T* psf, const float* staged, int
         return PsfNum<T>::load(psf, i);
 }
 
+namespace mk {
+constexpr int kMaxBands = (32 + kChunkGroups - 1) / kChunkGroups;   // <= 32 groups of kGroupW columns in a 128-wide PSF
+constexpr int kBandMaxChunks = 8;                                   // 128 rows / (kChunkHaloRows + 1) rounded up
+
+// Program of the masked tiled kernel (layout in masked_common.cuh, consumer blur_masked.cu): unsheared groups of 4 columns,
+// a 4-wide weight vector per row, zero where the PSF has no tap (the kernel skips those).  Block-wide; returns through
+// shared memory: chunks (<= 0: none built), weight vectors, segments.
+template <typename T, bool kStaged>
+__device__ void build_program(const T* psf, const float* sh_psf, int side, int normalize, float s, int centre, int ymin, int ymax,
+                              int xmin, int xmax, uint8_t* my_prog, int& out_chunks_n, int& out_steps, int& out_segs) {
+    __shared__ unsigned sh_occ[32 * 4];
+    __shared__ ChunkRec sh_chunks[kProgMaxChunks];
+    __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
+    __shared__ ChunkRec sh_band_chunks[kMaxBands * kBandMaxChunks];
+    __shared__ SegRec sh_band_segs[kMaxBands * kBandMaxChunks * kChunkGroups];
+    __shared__ int sh_band_count[kMaxBands];
+    __shared__ int sh_nchunks, sh_nsegs, sh_total_steps;
+    const int tid = threadIdx.x;
+    ChunkRec* out_chunks = reinterpret_cast<ChunkRec*>(my_prog);
+    if (tid == 0) {
+        sh_nchunks = 0;
+        sh_nsegs = 0;
+        sh_total_steps = 0;
+    }
+    __syncthreads();
+    const int ngroups = (xmax - xmin + kGroupW) / kGroupW;   // <= 32 for side <= 129
+    const int nrows_box = ymax - ymin + 1;
+    // 3a. per group: bitmask of the PSF rows holding a tap in the group's columns (rows 0..127 -> 4 words)
+    for (int k = tid; k < ngroups * 4; k += kCompactThreads) sh_occ[k] = 0u;
+    __syncthreads();
+    for (int k = tid; k < ngroups * nrows_box; k += kCompactThreads) {
+        const int g = k / nrows_box, y = ymin + k % nrows_box;
+        bool any = false;
+        for (int e = 0; e < kGroupW; ++e) {
+            const int x = xmin + g * kGroupW + e;
+            if (x < side) {
+                const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
+                const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                any |= (w != 0.0f);
+            }
+        }
+        if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
+    }
+    __syncthreads();
+    // 3b. cut the support into chunks of segments: one thread per band of kChunkGroups groups walks that band's rows
+    //     with 128-bit masks (find-first-set), then thread 0 concatenates the bands' chunk lists in band order
+    const int nbands = (ngroups + kChunkGroups - 1) / kChunkGroups;
+    if (tid < nbands) {
+        const int g0 = tid * kChunkGroups, g1 = min(g0 + kChunkGroups, ngroups);
+        unsigned band[4] = {0u, 0u, 0u, 0u};
+        for (int g = g0; g < g1; ++g)
+            for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
+        int cursor = ymin, nb = 0;
+        while (nb < kBandMaxChunks) {
+            int y0 = mask_first_from(band, cursor);
+            if (y0 < 0) break;
+            const int y1 = min(y0 + kChunkHaloRows, ymax);
+            ChunkRec c;
+            int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
+            for (int g = g0; g < g1; ++g) {
+                int f, l;
+                mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
+                if (f < 0) continue;
+                SegRec sg;
+                sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
+                sg.dy0 = (int16_t)(f - centre);
+                sg.nsteps = (int16_t)(l - f + 1);
+                sg.woff = 0;
+                lo = min(lo, f - centre);
+                hi = max(hi, l - centre);
+                xlo = min(xlo, (int)sg.dx0);
+                xhi = max(xhi, (int)sg.dx0 + kGroupW - 1);
+                sh_band_segs[(tid * kBandMaxChunks + nb) * kChunkGroups + nseg] = sg;
+                ++nseg;
+            }
+            c.dy_lo = (int16_t)lo; c.dy_hi = (int16_t)hi;
+            c.dx_lo = (int16_t)xlo; c.dx_hi = (int16_t)xhi;
+            c.nseg = (int16_t)nseg; c.wsteps = 0;
+            c.data_off = 0;
+            sh_band_chunks[tid * kBandMaxChunks + nb] = c;
+            ++nb;
+            cursor = y1 + 1;
+        }
+        // more rows left than kBandMaxChunks chunks can cover: no program (the generic kernel takes the PSF)
+        sh_band_count[tid] = (nb == kBandMaxChunks && mask_first_from(band, cursor) >= 0) ? -1 : nb;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nchunks = 0, nsegs = 0;
+        bool ok = true;
+        for (int bnd = 0; bnd < nbands && ok; ++bnd) {
+            const int nb = sh_band_count[bnd];
+            if (nb < 0 || nchunks + nb > kProgMaxChunks) { ok = false; break; }
+            for (int k = 0; k < nb; ++k) {
+                sh_chunks[nchunks] = sh_band_chunks[bnd * kBandMaxChunks + k];
+                for (int q = 0; q < kChunkGroups; ++q)
+                    sh_segs[nchunks * kChunkGroups + q] = sh_band_segs[(bnd * kBandMaxChunks + k) * kChunkGroups + q];
+                nsegs += sh_chunks[nchunks].nseg;
+                ++nchunks;
+            }
+        }
+        sh_nchunks = ok ? nchunks : -1;
+        sh_nsegs = nsegs;
+    }
+    __syncthreads();
+    int nchunks = sh_nchunks;
+    // 3c. offsets: weight vectors of a chunk's segments are laid out back to back
+    if (nchunks > 0) {
+        if (tid == 0) {
+            int data_off = (int)kProgHeaderBytes, total_steps = 0;
+            bool ok = true;
+            for (int ci = 0; ci < nchunks && ok; ++ci) {
+                int nw = 0;
+                for (int sgi = 0; sgi < sh_chunks[ci].nseg; ++sgi) {
+                    sh_segs[ci * kChunkGroups + sgi].woff = (int16_t)nw;
+                    nw += sh_segs[ci * kChunkGroups + sgi].nsteps;
+                }
+                total_steps += nw;
+                const int bytes = kChunkSegBytes + kStepBytes * (nw + 1);
+                if (nw > kChunkMaxSteps || data_off + bytes > (int)kProgBytes) { ok = false; break; }
+                sh_chunks[ci].wsteps = (int16_t)nw;
+                sh_chunks[ci].data_off = data_off;
+                data_off += bytes;
+            }
+            if (!ok) sh_nchunks = -1;
+            sh_total_steps = total_steps;
+        }
+        __syncthreads();
+        nchunks = sh_nchunks;
+    }
+    // 3d. write chunk records, segment records and weight vectors
+    if (nchunks > 0) {
+        for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
+        for (int ci = 0; ci < nchunks; ++ci) {
+            const ChunkRec c = sh_chunks[ci];
+            SegRec* seg_out = reinterpret_cast<SegRec*>(my_prog + c.data_off);
+            float* wout = reinterpret_cast<float*>(my_prog + c.data_off + kChunkSegBytes);
+            if (tid < kChunkSegBytes / (int)sizeof(SegRec)) {
+                SegRec sg;
+                sg.dx0 = 0; sg.dy0 = 0; sg.nsteps = 0; sg.woff = 0;
+                if (tid < c.nseg) sg = sh_segs[ci * kChunkGroups + tid];
+                seg_out[tid] = sg;
+            }
+            if (tid < kGroupW) wout[c.wsteps * kGroupW + tid] = 0.0f;     // the vector the kernel prefetches past the end
+            for (int sgi = 0; sgi < c.nseg; ++sgi) {
+                const SegRec sg = sh_segs[ci * kChunkGroups + sgi];
+                for (int k = tid; k < sg.nsteps * kGroupW; k += kCompactThreads) {
+                    const int step = k / kGroupW, e = k % kGroupW;
+                    const int x = sg.dx0 + centre + e, y = sg.dy0 + centre + step;
+                    float w = 0.0f;
+                    if (x < side) {
+                        const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
+                        w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                    }
+                    wout[(sg.woff + step) * kGroupW + e] = w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    out_chunks_n = sh_nchunks;
+    out_steps = sh_total_steps;
+    out_segs = sh_nsegs;
+}
+}  // namespace mk
+
 template <typename T, bool kStaged>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
@@ -146,7 +311,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
 
     const int n = blockIdx.x;
     if (n == 0 && threadIdx.x == 0) {
-        for (int k = 0; k < kSchedSlots; ++k) {
+        for (int k = 0; k < 2 * kSchedSlots; ++k) {      // masked kernel: slots 0-3, dense kernel: slots 4-7
             sched[k].next_tile = 0u;
             sched[k].done_ctas = 0u;
         }
@@ -260,7 +425,12 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     }
     int prog_G = 0, prog_k = 0;
     __syncthreads();
-    if (want_prog) {
+    // A PSF whose support fits one chunk of the masked kernel's program (every low-exposure PSF) takes that kernel: it is
+    // the faster one there; everything else gets the dense sheared program.
+    const bool small_psf = want_prog && ymax - ymin <= mk::kChunkHaloRows && xmax - xmin < mk::kChunkGroups * mk::kGroupW;
+    int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
+    if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
+    if (want_prog && !(small_psf && mk_chunks == 1)) {
         const int nrows_box = ymax - ymin + 1;
         // 3a. rank the candidates (group width 2 / 4) x (shear -kShearMax .. kShearMax) by a cost model: per sheared group
         //     the span of rows it occupies -> dense steps, window fills and chunks.
@@ -508,6 +678,15 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         }
     }
     int nchunks_final = want_prog ? sh_nchunks : -1;
+    if (small_psf && mk_chunks == 1) {           // masked program: group width 0 in the summary
+        nchunks_final = 1;
+        prog_G = 0;
+        prog_k = 0;
+        if (tid == 0) {
+            sh_total_steps = mk_steps;
+            sh_nsegs = mk_segs;
+        }
+    }
     if (nchunks_final <= 0) {
         flags |= DIB_META_NO_PROGRAM;
         nchunks_final = 0;

@@ -319,7 +319,9 @@ def test_mixed_batch_both_kernels_and_pitched_views(dib):
     idx = [0, 1, 2, -1]
     l0 = bf.launch_count()
     got = bf.blur_batch(srcs, ts, idx, outs=outs)
-    assert bf.launch_count() - l0 == 2            # one tiled launch + one exact-order launch
+    # one launch per tiled kernel in use (masked program: group width 0, dense program: 2 or 4) + one exact-order launch
+    kinds = {ts.meta[i].prog_group_w == 0 for i in (0, 2)}
+    assert bf.launch_count() - l0 == len(kinds) + 1
     for k in range(3):
         want = bo.manual_blur(imgs[k], bo.normalize_psf(psfs[idx[k]]))
         g = got[k].cpu().numpy()

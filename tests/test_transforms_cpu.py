@@ -195,12 +195,12 @@ def test_host_rules_without_a_gpu():
 
     # the gate of the in-kernel half path: only the normalize epilogue, aligned destinations, sides > 64, a tiled program
     class Meta(object):
-        def __init__(self, count=20, chunks=1, flags=0):
-            self.count, self.prog_chunks, self.flags = count, chunks, flags
+        def __init__(self, count=20, chunks=1, flags=0, group_w=0):
+            self.count, self.prog_chunks, self.flags, self.prog_group_w = count, chunks, flags, group_w
 
     class Ts(object):
         side = 128
-        meta = [Meta(), Meta(flags=_lib.META_NO_PROGRAM), Meta(count=0)]
+        meta = [Meta(), Meta(flags=_lib.META_NO_PROGRAM), Meta(count=0), Meta(count=200, chunks=4, group_w=2)]
 
     img = torch.zeros((3, 100, 131), dtype=torch.float16)
     ok = lambda **kw: bf._half_tiled_ok(kw.pop("images", [img]), Ts(), kw.pop("idx", [0]), kw.pop("outs", None), kw.pop("noise", None),
@@ -209,6 +209,7 @@ def test_host_rules_without_a_gpu():
     assert ok()
     assert ok(pad_mode=_lib.PAD_ZERO128) and not ok(pad_mode=_lib.PAD_REPLICATE256)
     assert not ok(idx=[1]) and not ok(idx=[2]) and not ok(idx=[-1])
+    assert not ok(idx=[3])          # a large PSF (dense program): the masked kernel owns the in-kernel half path
     assert not ok(clamp=[False]) and not ok(noise_sd=[0.1]) and not ok(gamma=[2.2]) and not ok(philox_seed=1)
     assert not ok(images=[torch.zeros((3, 64, 131), dtype=torch.float16)])
     assert not ok(images=[img.float()])
