@@ -137,6 +137,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in hardware, do not spin
 }
+// Producer-group wait: ONE thread polls the mbarrier (with a back-off), the other 127 block in a named barrier, which costs
+// no issue slots -- four producer warps spinning on try_wait took a seventh of the SM's issue slots from the compute warps.
+__device__ __forceinline__ void producer_wait(uint64_t* bar, uint32_t parity, int pt) {
+    if (pt == 0) {
+        uint32_t done = 0;
+        while (true) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+            if (done) break;
+            __nanosleep(96);
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(4 * 32) : "memory");
+}
 // TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -322,7 +340,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
     }
     float* drow = sm.tile + ro - cl;                     // drow[col] addresses image column col
     const uint32_t nb_row = (in_rows && !zero_row) ? (uint32_t)(xb_al - xa_al) * 4u : 0u;
-    if (wait_empty) mbar_wait(empty_bar, empty_parity);  // consumers released the stage that used this buffer
+    if (wait_empty) producer_wait(empty_bar, empty_parity, pt);  // consumers released the stage that used this buffer
     fence_proxy_async();   // order the consumers' generic-proxy reads of this buffer before the async-proxy writes
     if (pt == 0) {
         StageHdr h;
@@ -430,7 +448,7 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
         head[j] = (in_rows && !zero_row && xa + j < xa_al) ? gp[xa + j] : __half(0.0f);
         tail[j] = (in_rows && !zero_row && xb_al + j < xb1) ? gp[xb_al + j] : __half(0.0f);
     }
-    mbar_wait(landed, landed_parity);
+    producer_wait(landed, landed_parity, pt);
     float* drow = sm.tile + ro - cl;                  // drow[col] addresses image column col
     // Widen the aligned interiors in place.  A warp takes the rows its own lanes placed, one row at a time, a lane per
     // group of 8 elements: every lane first reads its 16 bytes of halves, then -- after a warp barrier -- writes its 32
@@ -624,7 +642,7 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
     const uint32_t tile = rowtab + kRowTabBytes;
     // The two compute warps that share an SM sub-partition (warp ids w and w + 4) walk the segments in opposite
     // orders: otherwise they run the same instruction sequence in lockstep and their load phases coincide.
-    const bool reverse = ((threadIdx.x >> 5) & 4) != 0;
+    const bool reverse = (((threadIdx.x >> 5) - kProducerWarps) & 4) != 0;
 #pragma unroll 1
     for (int sgi = 0; sgi < nseg; ++sgi) {
         const int sg = reverse ? nseg - 1 - sgi : sgi;
@@ -906,10 +924,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
 
     // Register budget: the launch splits the register file evenly over all warps; the producer warpgroup hands most of
     // its share back so that the compute warps can hold kR * kCC accumulators + kR * kWinW window values per thread.
-    if (warp >= kComputeWarps) {
+    if (warp < kProducerWarps) {        // producers are the lowest warp ids: the issue arbiter favours high ids
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         // ------------------------------------------------ producer warpgroup
-        const int pt = threadIdx.x - kComputeWarps * 32;
+        const int pt = threadIdx.x;
         Stage cur, nxt;
         int nfetch = 0;
         cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
@@ -924,7 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             const bool wait_empty = n >= 2;
             const uint32_t empty_parity = (uint32_t)(((n >> 1) - 1) & 1);
             // the float path waits inside issue_stage, after the row arithmetic
-            if ((kHalf || cur.tile < 0) && wait_empty) mbar_wait(&empty[b], empty_parity);
+            if ((kHalf || cur.tile < 0) && wait_empty) producer_wait(&empty[b], empty_parity, pt);
             const StageSmem sm = stage_smem(smem, b);
             if (cur.tile < 0) {
                 if (pt == 0) sm.hdr->tile = -1;
@@ -954,9 +972,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
         // ------------------------------------------------ compute warps
-        const int wrow = warp / kWarpCols, wcol = warp % kWarpCols;
+        const int cw = warp - kProducerWarps;
+        const int wrow = cw / kWarpCols, wcol = cw % kWarpCols;
         float2 acc[kR][kCC];
-        const uint32_t obuf = smem_u32(obuf_all + warp * 2 * kOutPitch);
+        const uint32_t obuf = smem_u32(obuf_all + cw * 2 * kOutPitch);
         for (int n = 0;; ++n) {
             const int b = n & 1;
             const StageSmem sm = stage_smem(smem, b);
