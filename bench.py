@@ -37,7 +37,7 @@ FRACTIONS = [1 / 18, 1 / 10, 1 / 5, 1 / 2, 1]
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-overlap", action="store_true",
@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-5 / fp16 records and the reference GPU loop")
+    ap.add_argument("--min-ms", type=float, default=50.0, help="device time to measure before the median K-step region is taken")
     return ap.parse_args()
 
 
@@ -233,125 +235,114 @@ def run_reference_arm(args, spec):
 
 
 # ------------------------------------------------------------------------------------------- own arm
-def run_own_arm(args, spec):
-    import torch
-    import torch.distributed as dist
-    import detectinblur_b200.blur_functions as bf
-    import detectinblur_b200.psf_ops as ops
-    from detectinblur_b200 import _lib
-    import ctypes
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = spec["batch"]
-
-    # ---- synthetic inputs: images as torch.rand (seed 1337 + rank), PSFs rasterised on the GPU from seeded trajectories
-    n_rot = 3     # rotating input batches: 3 x 102 MB of inputs (+ outputs) > 126 MB L2, nothing survives between steps
-    gen = torch.Generator(device="cpu").manual_seed(1337 + rank)
-    half = bool(spec.get("half"))
-    esize = 2 if half else 4
-    img_dtype = torch.float16 if half else torch.float32
-    host_batches = [torch.rand((B, C, H, W), generator=gen).to(img_dtype).pin_memory() for _ in range(n_rot)]
-    batches = [hb.to(dev) for hb in host_batches]
-    fused = bool(spec.get("fused_normalize"))
-    # results land in rows that start 16-byte aligned (pitch 1336 floats; 1344 for the padded batch of the fused workload),
-    # handed out as [:, :, :W] views -- what blur_batch allocates by default, and like the reference, whose result is a
-    # crop view of its padded accumulator (blur_functions.py:69)
-    quad = 16 // esize
-    # one result buffer per rotating input batch: consecutive steps share nothing but the (read-only) tap set
-    outs_rot = [torch.zeros((B, C, H, 1344 if fused else (W + quad - 1) // quad * quad), dtype=img_dtype, device=dev)
-                for _ in range(n_rot)]
-    outs = outs_rot[0]
-    out_views_rot = [[o[i, :, :, :W] for i in range(B)] for o in outs_rot]
-    norm_kw = dict(mean=[[0.485, 0.456, 0.406]] * B, std=[[0.229, 0.224, 0.225]] * B) if fused else {}
-    traj, fracs = make_trajectories(spec, seed=1337 * rank)
-    psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
-    psfs = psfs16.to(img_dtype)                 # stored-format values (fp16 grid) in the image dtype
-    host_psfs = psfs.cpu().pin_memory()
-    tapset = ops.compact_taps(psfs, normalize=True)
-    taps = tapset.counts
-    idx = list(range(B))
-
-    plans = [bf.prepare_blur([batches[r][i] for i in range(B)], tapset, idx, outs=out_views_rot[r], **norm_kw)
-             for r in range(n_rot)]
-    overlap = not args.no_overlap
-
-    def step(k):
-        plans[k % n_rot].run(overlap=overlap)      # one dib_blur_batch call: host planning + ONE tiled-kernel launch
-
-    for k in range(max(args.warmup, 3)):
-        step(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    l0 = bf.launch_count()
-    # Two events bracket the K steps.  (An event recorded between two launches orders the second after the whole first grid,
-    # which is exactly what overlapped steps avoid; with --no-overlap the result is the same either way.)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    torch.cuda.synchronize()
-    t_wall0 = time.time()
-    ev[0].record()
-    for k in range(args.steps):
-        step(k)
-    ev[1].record()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    if world > 1:
-        dist.barrier()
-    launches = bf.launch_count() - l0
-    elapsed_ms = ev[0].elapsed_time(ev[1])
-    per_step = np.array([elapsed_ms / args.steps])
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms / 1000.0)
-
-    # the same steps with every launch ordered after the previous one, for reference (not the reported value)
-    ordered_ms = None
-    if overlap:
-        n_ord = max(10, min(args.steps, 200))
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        o0.record()
-        for k in range(n_ord):
-            plans[k % n_rot].run(overlap=False)
-        o1.record()
-        torch.cuda.synchronize()
-        ordered_ms = o0.elapsed_time(o1) / n_ord
-
-    # ---- kernel duration, live: the K blur launches are the only work between the two events: average per launch
-    kern_ms = float(per_step.mean())
-    algo_bytes = ALGO_BYTES_PER_IMAGE * B * esize // 4
-    peaks = {}
+def load_peaks():
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % spec["name"])
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+        return {}
 
-    # ---- FP32 pipe probe (compute leg of the roofline: taps x pixels FMAs)
+
+class Workload(object):
+    """Device-resident inputs, tap set and prepared launches of one BASELINE config on this rank's GPU."""
+
+    def __init__(self, spec, dev, rank, n_rot=3):
+        import torch
+        import detectinblur_b200.blur_functions as bf
+        import detectinblur_b200.psf_ops as ops
+        self.spec, self.dev, self.n_rot = spec, dev, n_rot
+        B = self.B = spec["batch"]
+        self.half = bool(spec.get("half"))
+        self.esize = 2 if self.half else 4
+        self.dtype = torch.float16 if self.half else torch.float32
+        gen = torch.Generator(device="cpu").manual_seed(1337 + rank)
+        # rotating input batches: 3 x 102 MB of inputs (+ outputs) > 126 MB L2, nothing survives between steps
+        self.host_batches = [torch.rand((B, C, H, W), generator=gen).to(self.dtype).pin_memory() for _ in range(n_rot)]
+        self.batches = [hb.to(dev) for hb in self.host_batches]
+        self.fused = bool(spec.get("fused_normalize"))
+        # results land in rows that start 16-byte aligned (pitch 1336 floats; 1344 for the padded batch of the fused workload),
+        # handed out as [:, :, :W] views -- what blur_batch allocates by default, and like the reference, whose result is a
+        # crop view of its padded accumulator (blur_functions.py:69)
+        quad = self.quad = 16 // self.esize
+        self.out_w = 1344 if self.fused else (W + quad - 1) // quad * quad
+        self.outs_rot = [torch.zeros((B, C, H, self.out_w), dtype=self.dtype, device=dev) for _ in range(n_rot)]
+        views = [[o[i, :, :, :W] for i in range(B)] for o in self.outs_rot]
+        norm_kw = dict(mean=[[0.485, 0.456, 0.406]] * B, std=[[0.229, 0.224, 0.225]] * B) if self.fused else {}
+        traj, fracs = make_trajectories(spec, seed=1337 * rank)
+        psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
+        self.psfs = psfs16.to(self.dtype)                 # stored-format values (fp16 grid) in the image dtype
+        self.host_psfs = self.psfs.cpu().pin_memory()
+        self.tapset = ops.compact_taps(self.psfs, normalize=True)
+        self.taps = self.tapset.counts
+        self.kernels = sorted({"blur_masked_kernel" if m.prog_group_w == 0 else "blur_tiled_kernel" for m in self.tapset.meta})
+        self.plans = [bf.prepare_blur([self.batches[r][i] for i in range(B)], self.tapset, list(range(B)), outs=views[r], **norm_kw)
+                      for r in range(n_rot)]
+
+    def step(self, k, overlap):
+        self.plans[k % self.n_rot].run(overlap=overlap)      # one dib_blur_batch call: host planning + one launch per tiled kernel in use
+
+    @property
+    def algo_bytes(self):
+        return ALGO_BYTES_PER_IMAGE * self.B * self.esize // 4
+
+    @property
+    def fmas(self):
+        return float(sum(self.taps)) * C * H * W
+
+
+def time_steps(step, K, warmup, min_ms=50.0, max_regions=400):
+    """Times regions of exactly K steps with CUDA events until at least `min_ms` of device time and 5 regions have been
+    measured; the K launches of a region are replayed from a CUDA graph when capture works, so that the host's launch path
+    (ctypes, validation, descriptors) is out of a window that may be only a millisecond long.  Returns the region times."""
+    import torch
+    for k in range(max(warmup, 3)):
+        step(k)
+    torch.cuda.synchronize()
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(3):
+                step(k)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for k in range(K):
+                step(k)
+        graph = g
+    except Exception as exc:      # capture unsupported for this launch: time direct launches instead
+        sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % (str(exc).splitlines()[0],))
+        graph = None
+        torch.cuda.synchronize()
+
+    def region():
+        if graph is not None:
+            graph.replay()
+        else:
+            for k in range(K):
+                step(k)
+
+    region()
+    torch.cuda.synchronize()
+    times = []
+    total = 0.0
+    while (total < min_ms or len(times) < 5) and len(times) < max_regions:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        region()
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        times.append(t)
+        total += t
+    return times, graph is not None
+
+
+def fp32_probe_tflops(dev):
+    import torch
+    import ctypes
+    from detectinblur_b200 import _lib
     sink = torch.empty(148 * 8 * 256 * 2, device=dev)
     cnt = ctypes.c_uint64(0)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -362,61 +353,245 @@ def run_own_arm(args, spec):
     _lib.check(_lib.lib.dib_fp32_probe(2000, ctypes.c_void_p(sink.data_ptr()), ctypes.byref(cnt), st))
     e1.record()
     torch.cuda.synchronize()
-    fp32_tflops = 2.0 * cnt.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    fmas = float(sum(taps)) * C * H * W
-    t_hbm = algo_bytes / (hbm_peak * 1e9)
-    t_fma = 2.0 * fmas / (fp32_tflops * 1e12)
-    roof_frac_max = max(t_hbm, t_fma) / (kern_ms * 1e-3)
+    return 2.0 * cnt.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
-    # ---- end to end through the reference-facing API with HOST buffers
-    e2e = None
-    if not args.no_e2e:
-        # three streams take turns so that the H2D copy of step k + 1 overlaps the D2H copy of step k (PCIe is full duplex)
-        # and the host-side work of a step (tap read-back, descriptors) hides behind the copies of the other two;
-        # every step still moves its own inputs in and its own results out inside the timed region
-        n_streams = 3
-        host_outs = [torch.empty((B, C, H, (W + quad - 1) // quad * quad), dtype=img_dtype).pin_memory() for _ in range(n_streams)]
-        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-        e2e_steps = max(6, min(args.steps, 24))
 
-        def e2e_step(k):
-            st = streams[k % n_streams]
-            st.synchronize()                      # the step that used this stream's buffers two steps ago is complete
-            with torch.cuda.stream(st):
-                hb = host_batches[k % n_rot]
-                dbatch = hb.to(dev, non_blocking=True)
-                dpsf = host_psfs.to(dev, non_blocking=True)
-                images = [dbatch[i] for i in range(B)]
-                bf.blur_image_list(images, [{"blurring": True}] * B, [dpsf[i] for i in range(B)])
+def roofline_block(wl, kernel_ms, pipelined_ms, hbm_peak, peak_src, fp32_tflops):
+    """The roofline of SURVEY.md 8(d): the slower of bytes at the HBM peak and taps x pixels FMAs at the FP32 peak.
+    `kernel_ms` is the duration of one launch ordered after its predecessor (what ncu reports); `pipelined_ms` the time
+    per launch when consecutive independent batches overlap tail-to-head (what `value` is made of)."""
+    t_hbm = wl.algo_bytes / (hbm_peak * 1e9)
+    t_fma = 2.0 * wl.fmas / (fp32_tflops * 1e12)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl.spec["name"])
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    common = {"traffic": traffic, "kernel": "dib::" + "+".join(wl.kernels), "kernel_ms": kernel_ms, "kernel_ms_pipelined": pipelined_ms,
+              "algorithmic_bytes_per_launch": wl.algo_bytes, "fma_per_launch": wl.fmas, "fp32_probe_tflops": fp32_tflops,
+              "hbm_peak_gbs": hbm_peak, "t_hbm_ms": t_hbm * 1e3, "t_fp32_ms": t_fma * 1e3,
+              "frac_pipelined": max(t_hbm, t_fma) / (pipelined_ms * 1e-3) if pipelined_ms else None}
+    if t_hbm >= t_fma:
+        ach = wl.algo_bytes / (kernel_ms * 1e-3) / 1e9
+        return dict({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": peak_src}, **common)
+    ach = 2.0 * wl.fmas / (kernel_ms * 1e-3) / 1e12
+    return dict({"bound": "fp32", "achieved": ach, "peak": fp32_tflops, "unit": "TFLOP/s", "frac": ach / fp32_tflops,
+                 "peak_source": "dib_fp32_probe measured in this run (FFMA, non-tensor); nominal 74.4"}, **common)
+
+
+def e2e_variant(kind, wl, dev, world, steps):
+    """The metric end to end through the reference-facing call with pinned HOST buffers: H2D of the step's images and dense
+    PSFs, tap compaction, blur, D2H of the results, every step, on three streams taking turns (PCIe is full duplex).
+    kind: 'f32' float32 both ways (what the reference's float tensors are), 'f16' half both ways (the dtype engine.py:80
+    uploads), 'u8' bytes both ways (uploaded bytes are scaled on the device as to_tensor does, results come back as the
+    uint8 image of the --cpu_blur path)."""
+    import torch
+    import torch.distributed as dist
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+    B = wl.B
+    n_streams = 3
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    if kind == "u8":
+        hin = [(hb.float() * 255).to(torch.uint8).pin_memory() for hb in wl.host_batches]
+        hout = [torch.empty((B, C, H, W), dtype=torch.uint8).pin_memory() for _ in range(n_streams)]
+        dout = [torch.empty((B, C, H, W), dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+        comp = torch.float32
+        in_bytes, out_bytes = B * C * H * W, B * C * H * W
+    else:
+        comp = torch.float32 if kind == "f32" else torch.float16
+        es = 4 if kind == "f32" else 2
+        quad = 16 // es
+        pitch = (W + quad - 1) // quad * quad
+        hin = [hb.to(comp).pin_memory() for hb in wl.host_batches]
+        hout = [torch.empty((B, C, H, pitch), dtype=comp).pin_memory() for _ in range(n_streams)]
+        in_bytes, out_bytes = B * C * H * W * es, B * C * H * pitch * es
+    hpsf = wl.host_psfs.to(comp).pin_memory()
+    in_bytes += hpsf.numel() * hpsf.element_size()
+
+    def step(k):
+        st = streams[k % n_streams]
+        st.synchronize()                      # the step that used this stream's buffers three steps ago is complete
+        with torch.cuda.stream(st):
+            dbatch = hin[k % wl.n_rot].to(dev, non_blocking=True)
+            dpsf = hpsf.to(dev, non_blocking=True)
+            if kind == "u8":
+                dbatch = ops.u8_to_float(dbatch)
+            images = [dbatch[i] for i in range(B)]
+            bf.blur_image_list(images, [{"blurring": True}] * B, [dpsf[i] for i in range(B)])
+            if kind == "u8":
+                for i in range(B):
+                    ops.float_to_u8(images[i], out=dout[k % n_streams][i])
+                hout[k % n_streams].copy_(dout[k % n_streams], non_blocking=True)
+            else:
                 for i in range(B):
                     # results are [:, :, :W] views of row-aligned buffers: copy the whole buffer (one plain async memcpy per
                     # image) instead of letting torch gather the view with an extra device kernel first
                     r = images[i]
                     full = r.as_strided((C, H, r.stride(1)), (r.stride(0), r.stride(1), 1))
-                    host_outs[k % n_streams][i, :, :, :r.stride(1)].copy_(full, non_blocking=True)
+                    hout[k % n_streams][i, :, :, :r.stride(1)].copy_(full, non_blocking=True)
 
-        for k in range(6):
-            e2e_step(k)
-        torch.cuda.synchronize()
+    for k in range(6):
+        step(k)
+    torch.cuda.synchronize()
+    regions = []
+    for _ in range(3):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            e2e_step(k)
+        for k in range(steps):
+            step(k)
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        t = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([e2e_s], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "images/s",
-               "h2d_bytes_per_step": int(B * C * H * W * esize + B * 128 * 128 * esize), "d2h_bytes_per_step": int(B * C * H * ((W + quad - 1) // quad * quad) * esize),
-               "steps": e2e_steps, "api": "blur_image_list(images, blur_dicts, psfs) on pinned host buffers, %d streams" % n_streams,
-               "pcie_note": "measured on this pool: 46 GB/s per direction with both directions busy -> 3.6 k img/s ceiling for fp32"}
+            tt = torch.tensor([t], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        regions.append(t)
+    med = float(np.median(regions))
+    return {"value": world * B * steps / med, "unit": "images/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+            "steps": steps, "regions_s": regions, "io": kind,
+            "api": "blur_image_list(images, blur_dicts, psfs) on pinned host buffers, %d streams%s" % (
+                n_streams, "; psf_ops.u8_to_float / float_to_u8 around it" if kind == "u8" else "")}
+
+
+def reference_gpu_loop(wl, dev):
+    """The reference's own GPU loop (unmodified models/blur_functions.py:92-100, staged under baseline/_ref by
+    __graft_entry__.build()) on the same device-resident config-2 batch, fp32 and fp16: the path --gpu_blur users run today.
+    Reported only."""
+    import torch
+    ref_root = os.environ.get("DIB_REFERENCE_ROOT") or os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "models")):
+        return {"unavailable": "no reference tree at %s" % ref_root}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import refshim
+        refshim.install(ref_root)
+        import models.blur_functions as rbf
+    except Exception as exc:
+        return {"unavailable": "reference import failed: %s" % (str(exc).splitlines()[0],)}
+    out = {"source": "unmodified models/blur_functions.py blur_image_list from %s" % os.path.relpath(ref_root, ROOT), "batches": 3}
+    for name, dt in (("f32", torch.float32), ("f16", torch.float16)):
+        psfs = [wl.psfs[i].to(dt) for i in range(wl.B)]
+        times = []
+        for r in range(4):
+            images = [wl.batches[r % wl.n_rot][i].to(dt) for i in range(wl.B)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rbf.blur_image_list(images, [{"blurring": True}] * wl.B, list(psfs))
+            torch.cuda.synchronize()
+            if r > 0:
+                times.append(time.perf_counter() - t0)
+        out[name] = {"ms_per_batch": 1000.0 * float(np.median(times)), "images_per_s": wl.B / float(np.median(times))}
+    return out
+
+
+def run_own_arm(args, spec):
+    import torch
+    import torch.distributed as dist
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+    overlap = not args.no_overlap
+    wl = Workload(spec, dev, rank)
+    B = wl.B
+
+    # ---- the timed region: regions of exactly K steps, repeated until >= 50 ms have been measured; the median region counts
+    for k in range(Wm):
+        wl.step(k, overlap)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = bf.launch_count()
+    wl.step(0, overlap)
+    launches_per_step = bf.launch_count() - l0           # own kernels per step: one per tiled kernel in use
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    regions, used_graph = time_steps(lambda k: wl.step(k, overlap), K, Wm, min_ms=args.min_ms)
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    mine = [float(np.median(regions)), float(min(regions)), float(max(regions))]
+    per_rank = [mine]
+    if world > 1:
+        t = torch.tensor(mine, device=dev)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [[float(v) for v in g.tolist()] for g in gathered]
+    region_ms = max(p[0] for p in per_rank)               # MAX over ranks of each rank's median K-step region
+    slowest = int(np.argmax([p[0] for p in per_rank]))
+    value = world * B * K / (region_ms / 1000.0)
+
+    # ---- the same steps with every launch ordered after the previous one: the kernel's own duration (what ncu reports)
+    ordered_regions, _ = time_steps(lambda k: wl.step(k, False), K, 3, min_ms=min(args.min_ms, 30.0)) if overlap else (regions, used_graph)
+    kernel_ms = float(np.median(ordered_regions)) / K
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    fp32_tflops = fp32_probe_tflops(dev)
+    roofline = roofline_block(wl, kernel_ms, region_ms / K, hbm_peak, peak_src, fp32_tflops)
+
+    # ---- the other BASELINE configs, measured the same way (N = 1 only: they are records beside the headline, not the metric)
+    extra = {}
+    if world == 1 and not args.no_extras and spec["name"] == "cfg2":
+        for name in ("cfg3", "cfg5", "cfg2h"):
+            try:
+                sp = workload_spec(name, None)
+                w2 = Workload(sp, dev, rank)
+                k2 = max(5, min(K, 40 if name == "cfg3" else 200))
+                reg_o, g_o = time_steps(lambda k: w2.step(k, True), k2, 3, min_ms=40.0)
+                reg_s, _ = time_steps(lambda k: w2.step(k, False), k2, 3, min_ms=30.0)
+                ms_o, ms_s = float(np.median(reg_o)) / k2, float(np.median(reg_s)) / k2
+                extra[name] = {"workload": sp["desc"], "value": w2.B / (ms_o / 1000.0), "unit": "images/s", "steps": k2,
+                               "ms_per_step": ms_o, "ms_per_step_ordered": ms_s, "taps": w2.taps,
+                               "dtype": "f16 i/o, f32 accumulate" if w2.half else "f32", "cuda_graph": g_o,
+                               "roofline": roofline_block(w2, ms_s, ms_o, hbm_peak, peak_src, fp32_tflops)}
+                del w2
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                extra[name] = {"error": str(exc).splitlines()[0]}
+
+    # ---- end to end through the reference-facing API with HOST buffers
+    e2e, e2e_variants = None, {}
+    if not args.no_e2e:
+        e2e_steps = max(12, min(K, 48))
+        e2e = e2e_variant("f32", wl, dev, world, e2e_steps)
+        e2e["pcie_note"] = "measured on this pool: 46 GB/s per direction with both directions busy -> 3.6 k img/s ceiling for fp32"
+        for kind in ("f16", "u8"):
+            try:
+                e2e_variants[kind] = e2e_variant(kind, wl, dev, world, e2e_steps)
+            except Exception as exc:
+                e2e_variants[kind] = {"error": str(exc).splitlines()[0]}
+
+    # ---- the reference's own GPU loop on the same batch (rank 0, N = 1 only)
+    ref_loop = None
+    if world == 1 and rank == 0 and not args.no_extras and spec["name"] == "cfg2":
+        try:
+            ref_loop = reference_gpu_loop(wl, dev)
+        except Exception as exc:
+            ref_loop = {"unavailable": str(exc).splitlines()[0]}
 
     # ---- optional cross-shard verification: all-gather one checksum per rank (outside every timed region)
-    csum = ops.checksum(outs)
+    csum = ops.checksum(wl.outs_rot[0])
     sums = [int(csum.item()) & 0xFFFFFFFFFFFFFFFF]
     if world > 1:
         gathered = [torch.zeros_like(csum) for _ in range(world)]
@@ -426,49 +601,42 @@ def run_own_arm(args, spec):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            psf_host = host_psfs[B - 1].numpy().copy()
+            psf_host = wl.host_psfs[B - 1].float().numpy().copy()
             cores = os.cpu_count() or 1
             per_core = 3
             v, wall, cores = cpu_fourier_throughput(psf_host, per_core, None, cores)
             cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "%d images of 800x1333x3 (%d per core, one process per core), CPU Fourier blur port "
                              "(oracle/fourier_oracle.py), %.1f s wall" % (cores * per_core, per_core, wall)}
-        # the roofline leg that binds this workload: bytes at HBM peak vs taps x pixels FMAs at the FP32 peak
-        # kernel_ms is the average time per launch inside the timed region, where consecutive launches overlap tail-to-head;
-        # kernel_ms_ordered / frac_ordered are the same quantities with every launch ordered after the previous one
-        ordered = {}
-        if ordered_ms is not None:
-            ordered = {"kernel_ms_ordered": ordered_ms,
-                       "frac_ordered": max(t_hbm, t_fma) / (ordered_ms * 1e-3)}
-        common = {"traffic": traffic, "kernel": "dib::blur_tiled_kernel", "kernel_ms": kern_ms, **ordered,
-                  "algorithmic_bytes_per_launch": algo_bytes, "fma_per_launch": fmas, "fp32_probe_tflops": fp32_tflops,
-                  "hbm_peak_gbs": hbm_peak, "t_hbm_ms": t_hbm * 1e3, "t_fp32_ms": t_fma * 1e3,
-                  "frac_of_max_roofline": roof_frac_max}
-        if t_hbm >= t_fma:
-            roofline = dict({"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                             "peak_source": peak_src}, **common)
-        else:
-            ach_tf = 2.0 * fmas / (kern_ms * 1e-3) / 1e12
-            roofline = dict({"bound": "fp32", "achieved": ach_tf, "peak": fp32_tflops, "unit": "TFLOP/s", "frac": ach_tf / fp32_tflops,
-                             "peak_source": "dib_fp32_probe measured in this run (FFMA, non-tensor); nominal 74.4"}, **common)
         line = {
             "metric": "blurred images/sec (800x1333 RGB)", "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 i/o, f32 accumulate" if half else "f32",
+            "steps": K, "warmup": Wm, "ms_per_step": region_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 i/o, f32 accumulate" if wl.half else "f32",
             "data": "synthetic",
-            "config": {"workload": spec["desc"], "batch_per_gpu": B, "taps": taps,
+            "config": {"workload": spec["desc"], "batch_per_gpu": B, "taps": wl.taps, "kernels": wl.kernels,
+                       "timing": ("regions of exactly %d steps, each bracketed by CUDA events, repeated until >= %.0f ms of device time "
+                                  "(%d regions here); ms_per_step = MAX over ranks of each rank's MEDIAN region / %d; the launches of a "
+                                  "region are %s" % (K, args.min_ms, len(regions), K,
+                                                     "replayed from a CUDA graph (host launch path outside the window)" if used_graph
+                                                     else "issued directly (graph capture unavailable)")),
                        "step_overlap": ("consecutive steps are independent batches (own inputs, own outputs) launched with "
                                         "programmatic dependent launch: the tail of step k overlaps the ramp-up of step k + 1"
                                         if overlap else "every step is ordered after the previous one"),
-                       "ms_per_step_ordered": ordered_ms,
-                       "output_layout": "rows 16-byte aligned (pitch %d floats), returned as [:, :, :W] views" % outs.shape[3],
+                       "ms_per_step_ordered": kernel_ms,
+                       "input_layout": "the reference's: a list of contiguous CHW tensors (row pitch 1333 floats = 5332 B)",
+                       "output_layout": "rows 16-byte aligned (pitch %d elements), returned as [:, :, :W] views" % wl.out_w,
                        "l2": "3 rotating input batches (3 x %.0f MB in, %.0f MB out) > 126 MB L2" % (
-                           B * C * H * W * esize / 1e6, B * C * H * W * esize / 1e6),
+                           B * C * H * W * wl.esize / 1e6, B * C * H * W * wl.esize / 1e6),
                        "parallelism": "images sharded by rank, no collective on the hot path"},
+            "regions_ms": {"n": len(regions), "median": mine[0], "min": mine[1], "max": mine[2]},
+            "per_rank_region_ms": {"median_min_max": per_rank, "slowest_rank": slowest},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": launches,
+            "e2e_variants": e2e_variants,
+            "gpu_launches": launches_per_step * K,
             "roofline": roofline,
+            "extra": extra,
+            "reference_gpu_loop": ref_loop,
             "cpu_baseline": cpu,
             "checksums": ["%016x" % s for s in sums],
         }

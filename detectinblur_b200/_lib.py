@@ -82,7 +82,8 @@ class ResizeImage(ctypes.Structure):
 
 
 EXPORTS = ("dib_abi_version", "dib_last_error", "dib_device_info", "dib_tapset_layout_for", "dib_compact_taps",
-           "dib_blur_batch", "dib_rasterize_psf", "dib_generate_trajectories", "dib_unpack_psfs", "dib_resize_batch", "dib_checksum", "dib_fp32_probe")
+           "dib_blur_batch", "dib_rasterize_psf", "dib_generate_trajectories", "dib_unpack_psfs", "dib_resize_batch", "dib_checksum", "dib_fp32_probe",
+           "dib_u8_to_float", "dib_float_to_u8")
 
 
 def _load():
@@ -105,6 +106,8 @@ def _load():
     lib.dib_resize_batch.argtypes = [ctypes.POINTER(ResizeImage), i32, i32, ctypes.POINTER(i32), vp]
     lib.dib_checksum.argtypes = [vp, i32, i64, vp, i32, vp]
     lib.dib_fp32_probe.argtypes = [i32, vp, ctypes.POINTER(u64), vp]
+    lib.dib_u8_to_float.argtypes = [vp, vp, i32, i64, i32, i64, vp]
+    lib.dib_float_to_u8.argtypes = [vp, i32, vp, i64, i32, i64, vp]
     for name in EXPORTS:
         if name not in ("dib_last_error",):
             getattr(lib, name).restype = i32

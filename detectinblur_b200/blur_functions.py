@@ -308,8 +308,15 @@ def blur_image_list(images_GPU, blur_dicts, psfs_GPU, add_noise=False, noise_lev
         for k in members:
             pad_mode_for(side, int(images_GPU[k].shape[1]), int(images_GPU[k].shape[2]))
         psfs = torch.stack([psfs_GPU[k] for k in members])
-        if psf_dtype == img_dtype:
+        want_exact = _exact_default() if exact is None else exact
+        if psf_dtype == img_dtype and not (want_exact and psf_dtype == torch.float32):
+            # the compaction kernel's own normalisation: the sum accumulated in fp64 and rounded once, which equals torch's
+            # result for every PSF on the fp16 grid summing to at most 1 (all stored / generated PSFs); a general fp32 PSF
+            # may differ from torch's reduction tree by one ulp of the sum
             tapset = psf_ops.compact_taps(psfs, normalize=True)
+        elif psf_dtype == img_dtype:
+            # exact=True promises the reference's bits for ANY fp32 PSF: normalise with torch itself, PSF by PSF (:98)
+            tapset = psf_ops.compact_taps(torch.stack([p / p.sum() for p in psfs]), normalize=False)
         else:
             # the reference multiplies by the 0-dim normalised PSF element cast to the image dtype: normalise in the
             # PSF dtype, cast, then compact, so tap weights carry exactly that rounding

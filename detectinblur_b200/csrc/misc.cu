@@ -50,7 +50,71 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, float a, flo
     if (s == 12345.678f) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true in practice; keeps the chain alive
 }
 
+// uint8 <-> float image planes, four pixels per thread.  Rows may be pitched on the float side (the blur's results are
+// [:, :, :W] views of row-aligned buffers); the uint8 side is dense.
+template <typename F>
+__global__ void u8_to_float_kernel(const uint8_t* __restrict__ src, F* __restrict__ dst, int64_t rows, int W, int64_t dst_pitch) {
+    const int quads = (W + 3) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * quads; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / quads;
+        const int x0 = (int)(i - r * quads) * 4;
+        const uint8_t* s = src + r * W + x0;
+        F* d = dst + r * dst_pitch + x0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x0 + j < W) d[j] = (F)__fdiv_rn((float)s[j], 255.0f);      // torchvision's to_tensor: byte / 255 in fp32
+    }
+}
+template <typename F>
+__global__ void float_to_u8_kernel(const F* __restrict__ src, uint8_t* __restrict__ dst, int64_t rows, int W, int64_t src_pitch) {
+    const int quads = (W + 3) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * quads; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / quads;
+        const int x0 = (int)(i - r * quads) * 4;
+        const F* s = src + r * src_pitch + x0;
+        uint8_t* d = dst + r * W + x0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x0 + j < W) {
+                const float v = fminf(fmaxf(__fmul_rn((float)s[j], 255.0f), 0.0f), 255.0f);
+                d[j] = (uint8_t)v;                                          // truncation, as numpy's astype(uint8)
+            }
+    }
+}
+
 }  // namespace dib
+
+extern "C" int dib_u8_to_float(const uint8_t* src, void* dst, int dst_dtype, int64_t rows, int W, int64_t dst_row_pitch, void* stream) {
+    using namespace dib;
+    DIB_CHECK_ARG(src != nullptr && dst != nullptr && rows >= 0 && W > 0 && dst_row_pitch >= W, "dib_u8_to_float: bad arguments");
+    DIB_CHECK_ARG(dst_dtype == DIB_F32 || dst_dtype == DIB_F16, "dib_u8_to_float: destination must be float32 or float16");
+    if (rows == 0) return DIB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t work = rows * ((W + 3) / 4);
+    const int blocks = (int)(work / 256 + 1 < 148 * 16 ? work / 256 + 1 : 148 * 16);
+    if (dst_dtype == DIB_F32)
+        u8_to_float_kernel<float><<<blocks, 256, 0, st>>>(src, static_cast<float*>(dst), rows, W, dst_row_pitch);
+    else
+        u8_to_float_kernel<__half><<<blocks, 256, 0, st>>>(src, static_cast<__half*>(dst), rows, W, dst_row_pitch);
+    DIB_CUDA(cudaGetLastError());
+    return DIB_OK;
+}
+
+extern "C" int dib_float_to_u8(const void* src, int src_dtype, uint8_t* dst, int64_t rows, int W, int64_t src_row_pitch, void* stream) {
+    using namespace dib;
+    DIB_CHECK_ARG(src != nullptr && dst != nullptr && rows >= 0 && W > 0 && src_row_pitch >= W, "dib_float_to_u8: bad arguments");
+    DIB_CHECK_ARG(src_dtype == DIB_F32 || src_dtype == DIB_F16, "dib_float_to_u8: source must be float32 or float16");
+    if (rows == 0) return DIB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t work = rows * ((W + 3) / 4);
+    const int blocks = (int)(work / 256 + 1 < 148 * 16 ? work / 256 + 1 : 148 * 16);
+    if (src_dtype == DIB_F32)
+        float_to_u8_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(src), dst, rows, W, src_row_pitch);
+    else
+        float_to_u8_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(src), dst, rows, W, src_row_pitch);
+    DIB_CUDA(cudaGetLastError());
+    return DIB_OK;
+}
 
 extern "C" int dib_checksum(const void* data, int dtype, int64_t n_elements, uint64_t* out, int accumulate, void* stream) {
     using namespace dib;

@@ -160,8 +160,14 @@ def fused_blur_normalize(images_GPU, blur_dicts, psfs_GPU, newMeans=None, newSTD
             raise ValueError("fused_blur_normalize needs PSFs of one container size per batch")
         for k in blurred:
             blur_functions.pad_mode_for(int(psfs_GPU[k].shape[0]), sizes[k][0], sizes[k][1])
-        stack = torch.stack([psfs_GPU[k].to(dtype) for k in blurred])
-        tapset = psf_ops.compact_taps(stack, normalize=True)
+        psf_dtypes = {psfs_GPU[k].dtype for k in blurred}
+        if psf_dtypes == {dtype}:
+            tapset = psf_ops.compact_taps(torch.stack([psfs_GPU[k] for k in blurred]), normalize=True)
+        else:
+            # the reference normalises in the PSF's dtype and multiplies by the 0-dim element cast to the image dtype
+            # (blur_functions.py:98, :67): normalise first, cast, then compact -- as blur_image_list does
+            dense = torch.stack([(psfs_GPU[k] / psfs_GPU[k].sum()).to(dtype) for k in blurred])
+            tapset = psf_ops.compact_taps(dense, normalize=False)
         for j, k in enumerate(blurred):
             idx[k] = j
     if min_size is not None:
@@ -192,6 +198,10 @@ class GeneralizedRCNNTransform(torch.nn.Module):
         self.max_size = max_size
         self.image_mean = image_mean
         self.image_std = image_std
+        if crop_images:
+            # batch_images' crop branch (net_transforms.py:218-236: crop every image to the batch's smallest extent) is a
+            # training augmentation of the detector; silently padding instead would change the batch shapes
+            raise NotImplementedError("crop_images=True is not mirrored here; use the reference's transform for that augmentation")
         self.crop_images = crop_images
         self.training = training
         self.normalize_images = normalize_images
@@ -221,6 +231,8 @@ class GeneralizedRCNNTransform(torch.nn.Module):
                 else:
                     means, stds = [self.image_mean] * len(images), [self.image_std] * len(images)
             return resize_normalize_batch(images, target_sizes, float(self.max_size), means, stds), targets
+        # anything else (CPU tensors, other dtypes) runs the reference's own torch sequence: this is the transform of the
+        # detector's input, not the blur path, and must keep working for inputs the CUDA pass does not take
         for i in range(len(images)):
             image = images[i]
             if image.dim() != 3:

@@ -224,3 +224,37 @@ def checksum(tensor, out=None, accumulate=False):
         _lib.check(_lib.lib.dib_checksum(ctypes.c_void_p(t.data_ptr()), _TORCH_TO_DIB[t.dtype], t.numel(),
                                          ctypes.c_void_p(out.data_ptr()), 1 if accumulate else 0, _stream_ptr(t.device)))
     return out
+
+
+def u8_to_float(images_u8, dtype=torch.float32, out=None):
+    """uint8 CUDA tensor [..., H, W] -> float tensor of the same shape, byte / 255 (torchvision's to_tensor scaling, what
+    the reference's DataLoader hands engine.py:80): lets a caller upload bytes -- a quarter of the float32 traffic."""
+    _require_cuda(images_u8, "images_u8")
+    if images_u8.dtype != torch.uint8:
+        raise TypeError("u8_to_float takes uint8 tensors")
+    src = images_u8.contiguous()
+    W = int(src.shape[-1])
+    rows = src.numel() // W
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib.dib_u8_to_float(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()), _TORCH_TO_DIB[out.dtype],
+                                            rows, W, out.stride(-2) if out.dim() > 1 else W, _stream_ptr(src.device)))
+    return out
+
+
+def float_to_u8(image, out=None):
+    """float CUDA tensor [C, H, W] (rows may be pitched) -> dense uint8 tensor: 255 * x clipped to [0, 255] and truncated, the
+    uint8 image the --cpu_blur path returns (motion_blur/blur_image.py:147)."""
+    _require_cuda(image, "image")
+    if image.dtype not in (torch.float32, torch.float16) or image.dim() != 3 or image.stride(2) != 1:
+        raise TypeError("float_to_u8 takes float32 / float16 [C, H, W] tensors with contiguous rows")
+    C, H, W = (int(v) for v in image.shape)
+    if C > 1 and image.stride(0) != image.stride(1) * H:
+        image = image.contiguous()
+    if out is None:
+        out = torch.empty((C, H, W), dtype=torch.uint8, device=image.device)
+    with torch.cuda.device(image.device):
+        _lib.check(_lib.lib.dib_float_to_u8(ctypes.c_void_p(image.data_ptr()), _TORCH_TO_DIB[image.dtype], ctypes.c_void_p(out.data_ptr()),
+                                            C * H, W, image.stride(1), _stream_ptr(image.device)))
+    return out

@@ -139,7 +139,10 @@ DIB_API int dib_device_info(int* sm_count, int* cc);
  *   psfs        n dense side x side PSFs, `psf_stride` elements apart, dtype DIB_F32 or DIB_F16
  *   normalize   1: divide by the PSF's sum in the PSF dtype (blur_image_list); 0: PSF already normalised (manual_blur)
  *   tapset      caller-owned device buffer of dib_tapset_layout(...).total_bytes
- * Taps come out in row-major order with bit-exact weights; meta carries counts, extents and PCA moments.
+ * Taps come out in row-major order; with normalize = 0 the weights are the PSF's own values, with normalize = 1 the sum is
+ * accumulated in fp64 and rounded once to the PSF dtype -- torch's result for every PSF on the fp16 grid that sums to at most
+ * 1 (all stored / generated PSFs); a general fp32 PSF can differ from torch's reduction tree by one ulp of the sum (the
+ * wrapper's exact mode normalises such PSFs with torch and passes normalize = 0).  meta carries counts, extents, PCA moments.
  */
 DIB_API int dib_tapset_layout_for(int n_psfs, int max_taps, dib_tapset_layout* out);
 DIB_API int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int side, int64_t psf_stride, int normalize,
@@ -229,6 +232,15 @@ DIB_API int dib_unpack_psfs(const uint32_t* taps, const int64_t* offsets, int n,
  * `out` is one uint64 in device memory; accumulate != 0 adds to its current value.
  */
 DIB_API int dib_checksum(const void* data, int dtype, int64_t n_elements, uint64_t* out, int accumulate, void* stream);
+
+/*
+ * uint8 <-> float image planes.  dib_u8_to_float replaces torchvision's to_tensor scaling (byte / 255, the input of
+ * engine.py:80's upload) on the device, so that a caller can upload bytes instead of floats; dib_float_to_u8 is the uint8
+ * result of the --cpu_blur path (motion_blur/blur_image.py:147: 255 * x, clipped, truncated).  `rows` counts image rows over
+ * all channels (C * H); the float side may be pitched (`*_row_pitch` in elements), the uint8 side is dense.
+ */
+DIB_API int dib_u8_to_float(const uint8_t* src, void* dst, int dst_dtype, int64_t rows, int W, int64_t dst_row_pitch, void* stream);
+DIB_API int dib_float_to_u8(const void* src, int src_dtype, uint8_t* dst, int64_t rows, int W, int64_t src_row_pitch, void* stream);
 
 /*
  * FP32 FMA-pipe probe used by bench.py for the compute roofline: launches `iters` dependent-chain-free FFMA

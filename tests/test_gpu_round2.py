@@ -1,0 +1,210 @@
+"""GPU parity tests added in round 2 (run on the B200 box: pytest -m gpu): the tiled kernels against the ORACLE at BASELINE's
+full image size, the exact PSF batches bench.py builds, the reference's own loop on CUDA tensors (when the staged reference
+tree is present), dilated PSFs beyond 1024 taps, pitched inputs, small overlapped grids and the uint8 conversions."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from oracle import blur_oracle as bo  # noqa: E402
+from oracle import psf_oracle as po  # noqa: E402
+
+TOL_FP32 = 1e-5      # north_star: within max-abs 1e-5 of the reference's fp32 GPU loop
+TOL_FP16 = 5e-3      # fp16 images: fp32 accumulation + one rounding vs the reference's half loop
+
+
+@pytest.fixture(scope="module")
+def dib():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import detectinblur_b200.blur_functions as bf
+    import detectinblur_b200.psf_ops as ops
+    return bf, ops
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _bench_psfs(name):
+    """The PSFs bench.py blurs with on rank 0 (same seeded trajectories), rasterised by the oracle."""
+    sys.path.insert(0, ROOT)
+    import bench
+    spec = bench.workload_spec(name, None)
+    traj, fr = bench.make_trajectories(spec, seed=0)
+    return [po.crop128(po.center(po.rasterize(x, f, 256), 256).astype(np.float16)).astype(np.float32) for x, f in zip(traj, fr)], spec
+
+
+@pytest.mark.parametrize("which", ["P1E0", "P3E4"])
+def test_tiled_kernels_vs_oracle_at_baseline_size(dib, which):
+    """3 x 800 x 1333 directly against the oracle's numpy gather (no detour over the exact-order kernel): one low-exposure
+    PSF (masked kernel, ~16 taps) and one high-exposure P3 PSF (dense sheared kernel, ~250 taps, several chunks)."""
+    bf, ops = dib
+    np.random.seed(11 if which == "P1E0" else 12)
+    expl, frac = (0.005, 1 / 18) if which == "P1E0" else (0.00005, 1.0)
+    psf16, _ = po.stored_psf(expl, frac, np.random)
+    psfn = bo.normalize_psf(po.crop128(psf16).astype(np.float32))
+    img = np.random.default_rng(5).random((3, 800, 1333), dtype=np.float32)
+    want = bo.manual_blur(img, psfn)
+    ts = ops.compact_taps(_cuda(psfn), normalize=False)
+    assert (ts.meta[0].prog_group_w == 0) == (which == "P1E0")        # which tiled kernel the PSF is routed to
+    if which == "P3E4":
+        assert ts.meta[0].prog_chunks > 1
+    got = bf.blur_batch([_cuda(img)], ts, [0])[0].cpu().numpy()
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL_FP32
+    exact = bf.blur_batch([_cuda(img)], ts, [0], exact=True)[0].cpu().numpy()
+    assert np.array_equal(exact, want)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_bench_batches(dib, name):
+    """The exact batches bench.py times (BASELINE configs 2 and 3: batch 8 / 16 of 3 x 800 x 1333 with its PSF sets): the GPU
+    rasteriser reproduces the oracle's PSFs bit for bit, every image of the tiled launch is within 1e-5 of the exact-order
+    kernel, and one image of the batch is checked against the oracle itself."""
+    bf, ops = dib
+    import bench
+    psfs, spec = _bench_psfs(name)
+    B = spec["batch"]
+    traj, fr = bench.make_trajectories(spec, seed=0)
+    gpu_psfs = ops.rasterize_psfs(traj, fr, "cuda", dtype=torch.float16)
+    assert np.array_equal(gpu_psfs.float().cpu().numpy(), np.stack(psfs))
+    gen = torch.Generator(device="cpu").manual_seed(1337)
+    batch = torch.rand((B, 3, 800, 1333), generator=gen).cuda()
+    ts = ops.compact_taps(gpu_psfs.float(), normalize=True)
+    imgs = [batch[i] for i in range(B)]
+    got = bf.blur_batch(imgs, ts, list(range(B)))
+    exact = bf.blur_batch(imgs, ts, list(range(B)), exact=True)
+    for i in range(B):
+        assert (got[i] - exact[i]).abs().max().item() <= TOL_FP32, i
+    k = B - 1
+    want = bo.manual_blur(batch[k].cpu().numpy(), bo.normalize_psf(psfs[k]))
+    assert np.abs(got[k].cpu().numpy().astype(np.float64) - want).max() <= TOL_FP32
+    assert np.array_equal(exact[k].cpu().numpy(), want)
+
+
+def test_reference_gpu_loop_on_cuda_tensors(dib):
+    """The reference's own models/blur_functions.manual_blur on CUDA tensors (the code --gpu_blur runs) against this path:
+    fp32 within 1e-5 (tiled) / bit-identical (exact-order kernel), fp16 within 5e-3 / bit-identical.  Needs the reference
+    tree that __graft_entry__.build() stages under baseline/_ref (or DIB_REFERENCE_ROOT)."""
+    bf, ops = dib
+    ref_root = os.environ.get("DIB_REFERENCE_ROOT") or os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "models")):
+        pytest.skip("no staged reference tree at %s" % ref_root)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import refshim
+    refshim.install(ref_root)
+    import models.blur_functions as rbf
+    np.random.seed(4)
+    for expl, frac in ((0.005, 1 / 5), (0.00005, 1 / 2)):
+        psf16, _ = po.stored_psf(expl, frac, np.random)
+        psf = _cuda(po.crop128(psf16).astype(np.float32))
+        psfn = psf / psf.sum()
+        img = torch.rand((3, 300, 500), generator=torch.Generator().manual_seed(9)).cuda()
+        want = rbf.manual_blur(img, psfn).contiguous()
+        got = bf.manual_blur(img, psfn)
+        assert (got - want).abs().max().item() <= TOL_FP32
+        assert torch.equal(bf.manual_blur(img, psfn, exact=True), want)
+        want16 = rbf.manual_blur(img.half(), psfn.half()).contiguous()
+        assert (bf.manual_blur(img.half(), psfn.half()).float() - want16.float()).abs().max().item() <= TOL_FP16
+        assert torch.equal(bf.manual_blur(img.half(), psfn.half(), exact=True), want16)
+    # the in-place list call, with a skipped entry
+    imgs = [torch.rand((3, 200, 260), generator=torch.Generator().manual_seed(k)).cuda() for k in range(3)]
+    ref_imgs = [t.clone() for t in imgs]
+    dicts = [{"blurring": True}, {"blurring": False}, {"blurring": True}]
+    psfs = [psf, torch.zeros(1).cuda(), psf]
+    rbf.blur_image_list(ref_imgs, dicts, psfs)
+    bf.blur_image_list(imgs, dicts, psfs)
+    for a, b in zip(imgs, ref_imgs):
+        assert (a - b).abs().max().item() <= TOL_FP32
+
+
+def test_dilated_psf_above_1024_taps(dib):
+    """--dilate_psf (transforms.py:338-342: gaussian_filter, sigma up to 3) routinely leaves more than 1024 nonzero cells;
+    the tap list grows to hold them and both kernels still match the oracle."""
+    bf, ops = dib
+    from scipy.ndimage import gaussian_filter
+    np.random.seed(2)
+    psf16, _ = po.stored_psf(0.00005, 1.0, np.random)
+    psf = gaussian_filter(po.crop128(psf16).astype(np.float64), sigma=3.0).astype(np.float16).astype(np.float32)
+    assert np.count_nonzero(psf) > 1024
+    psfn = bo.normalize_psf(psf)
+    ts = ops.compact_taps(_cuda(psf), normalize=True)
+    assert ts.counts[0] == np.count_nonzero(psfn) and ts.max_taps >= ts.counts[0]
+    img = np.random.default_rng(8).random((3, 150, 210), dtype=np.float32)
+    want = bo.manual_blur(img, psfn)
+    got = bf.blur_batch([_cuda(img)], ts, [0])[0].cpu().numpy()
+    assert np.abs(got.astype(np.float64) - want).max() <= TOL_FP32
+    assert np.array_equal(bf.blur_batch([_cuda(img)], ts, [0], exact=True)[0].cpu().numpy(), want)
+
+
+def test_pitched_and_unpitched_inputs_agree(dib):
+    """The same pixels as a contiguous CHW tensor (the reference's layout, 5332-byte rows at W = 1333) and as a [:, :, :W]
+    view of a 16-byte-pitched buffer, through both tiled kernels: identical results (the 1-D TMA boxes of the dense kernel
+    and the per-row bulk copies of the masked kernel only see different row phases)."""
+    bf, ops = dib
+    np.random.seed(6)
+    psfs = []
+    for expl, frac in ((0.005, 1 / 10), (0.00005, 1.0)):
+        p16, _ = po.stored_psf(expl, frac, np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    ts = ops.compact_taps(_cuda(np.stack(psfs)), normalize=True)
+    assert ts.meta[0].prog_group_w == 0 and ts.meta[1].prog_group_w != 0
+    img = torch.rand((3, 211, 1333), generator=torch.Generator().manual_seed(1)).cuda()
+    pitched = torch.zeros((3, 211, 1344)).cuda()
+    pitched[:, :, :1333] = img
+    shifted = torch.zeros((3, 211, 1340)).cuda()[:, :, 3:1336]          # rows start 12 bytes off a 16-byte boundary
+    shifted.copy_(img)
+    for k in (0, 1):
+        a = bf.blur_batch([img], ts, [k])[0]
+        b = bf.blur_batch([pitched[:, :, :1333]], ts, [k])[0]
+        c = bf.blur_batch([shifted], ts, [k])[0]
+        assert torch.equal(a, b) and torch.equal(a, c)
+        want = bo.manual_blur(img.cpu().numpy(), bo.normalize_psf(psfs[k]))
+        assert np.abs(a.cpu().numpy().astype(np.float64) - want).max() <= TOL_FP32
+
+
+def test_small_grids_overlapped_for_a_thousand_launches(dib):
+    """DIB_ALGO_OVERLAP with grids smaller than the machine (fewer tiles than SMs) and only two rotating output buffers:
+    such launches order themselves after their predecessor (a small grid could otherwise be co-resident with many
+    successors), so 1000 overlapped launches give bit for bit what ordered launches give."""
+    bf, ops = dib
+    np.random.seed(3)
+    p16, _ = po.stored_psf(0.005, 1 / 5, np.random)
+    big16, _ = po.stored_psf(0.00005, 1.0, np.random)
+    ts = ops.compact_taps(_cuda(np.stack([po.crop128(p16).astype(np.float32), po.crop128(big16).astype(np.float32)])), normalize=True)
+    g = torch.Generator().manual_seed(2)
+    imgs = [[torch.rand((3, 100, 300), generator=g).cuda(), torch.rand((3, 90, 500), generator=g).cuda()] for _ in range(2)]
+    outs = [[torch.zeros_like(t) for t in pair] for pair in imgs]
+    plans = [bf.prepare_blur(imgs[r], ts, [0, 1], outs=outs[r]) for r in range(2)]
+    want = [[t.clone() for t in plans[r].run()] for r in range(2)]
+    torch.cuda.synchronize()
+    for o in outs:
+        for t in o:
+            t.zero_()
+    for k in range(1000):
+        plans[k % 2].run(overlap=True)
+    torch.cuda.synchronize()
+    for r in range(2):
+        for a, b in zip(outs[r], want[r]):
+            assert torch.equal(a, b)
+
+
+def test_u8_conversions(dib):
+    bf, ops = dib
+    g = torch.Generator().manual_seed(7)
+    u8 = torch.randint(0, 256, (2, 3, 37, 101), generator=g, dtype=torch.uint8).cuda()
+    f = ops.u8_to_float(u8)
+    assert torch.equal(f, u8.float() / 255)                    # torchvision's to_tensor scaling, bit for bit
+    assert torch.equal(ops.u8_to_float(u8, dtype=torch.float16), (u8.float() / 255).half())
+    x = torch.rand((3, 50, 1333), generator=g).cuda() * 1.2 - 0.1
+    pitched = torch.zeros((3, 50, 1336)).cuda()[:, :, :1333]
+    pitched.copy_(x)
+    want = (x * 255).clamp(0, 255).to(torch.uint8)             # numpy astype(uint8) truncation of the clipped product
+    assert torch.equal(ops.float_to_u8(x), want) and torch.equal(ops.float_to_u8(pitched), want)
+    with pytest.raises(TypeError):
+        ops.u8_to_float(x)
