@@ -199,12 +199,15 @@ def test_u8_conversions(dib):
     g = torch.Generator().manual_seed(7)
     u8 = torch.randint(0, 256, (2, 3, 37, 101), generator=g, dtype=torch.uint8).cuda()
     f = ops.u8_to_float(u8)
-    assert torch.equal(f, u8.float() / 255)                    # torchvision's to_tensor scaling, bit for bit
-    assert torch.equal(ops.u8_to_float(u8, dtype=torch.float16), (u8.float() / 255).half())
+    # torchvision's to_tensor scaling runs on the CPU (DataLoader workers): an IEEE division by 255, bit for bit (torch's
+    # CUDA division by a scalar multiplies by the reciprocal instead and differs in the last bit for some bytes)
+    ref = u8.cpu().float().div(255)
+    assert torch.equal(f.cpu(), ref)
+    assert torch.equal(ops.u8_to_float(u8, dtype=torch.float16).cpu(), ref.half())
     x = torch.rand((3, 50, 1333), generator=g).cuda() * 1.2 - 0.1
     pitched = torch.zeros((3, 50, 1336)).cuda()[:, :, :1333]
     pitched.copy_(x)
-    want = (x * 255).clamp(0, 255).to(torch.uint8)             # numpy astype(uint8) truncation of the clipped product
-    assert torch.equal(ops.float_to_u8(x), want) and torch.equal(ops.float_to_u8(pitched), want)
+    want = torch.from_numpy(np.clip(x.cpu().numpy() * np.float32(255), 0, 255).astype(np.uint8))   # clipped product, truncated
+    assert torch.equal(ops.float_to_u8(x).cpu(), want) and torch.equal(ops.float_to_u8(pitched).cpu(), want)
     with pytest.raises(TypeError):
         ops.u8_to_float(x)
