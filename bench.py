@@ -245,7 +245,7 @@ def load_peaks():
 class Workload(object):
     """Device-resident inputs, tap set and prepared launches of one BASELINE config on this rank's GPU."""
 
-    def __init__(self, spec, dev, rank, n_rot=3):
+    def __init__(self, spec, dev, rank, n_rot=3, dense_only=False, pitched=False):
         import torch
         import detectinblur_b200.blur_functions as bf
         import detectinblur_b200.psf_ops as ops
@@ -258,6 +258,11 @@ class Workload(object):
         # rotating input batches: 3 x 102 MB of inputs (+ outputs) > 126 MB L2, nothing survives between steps
         self.host_batches = [torch.rand((B, C, H, W), generator=gen).to(self.dtype).pin_memory() for _ in range(n_rot)]
         self.batches = [hb.to(dev) for hb in self.host_batches]
+        if pitched:      # the same pixels as [:, :, :, :W] views of buffers whose rows start 16-byte aligned (pitch 1344 elements)
+            wide = [torch.zeros((B, C, H, 1344), dtype=self.dtype, device=dev) for _ in range(n_rot)]
+            for wbuf, b in zip(wide, self.batches):
+                wbuf[:, :, :, :W] = b
+            self.batches = [wbuf[:, :, :, :W] for wbuf in wide]
         self.fused = bool(spec.get("fused_normalize"))
         # results land in rows that start 16-byte aligned (pitch 1336 floats; 1344 for the padded batch of the fused workload),
         # handed out as [:, :, :W] views -- what blur_batch allocates by default, and like the reference, whose result is a
@@ -271,7 +276,7 @@ class Workload(object):
         psfs16 = ops.rasterize_psfs(traj, fracs, dev, canvas=256, center=True, out_side=128, dtype=torch.float16)
         self.psfs = psfs16.to(self.dtype)                 # stored-format values (fp16 grid) in the image dtype
         self.host_psfs = self.psfs.cpu().pin_memory()
-        self.tapset = ops.compact_taps(self.psfs, normalize=True)
+        self.tapset = ops.compact_taps(self.psfs, normalize=True, dense_only=dense_only)
         self.taps = self.tapset.counts
         self.kernels = sorted({"blur_masked_kernel" if m.prog_group_w == 0 else "blur_tiled_kernel" for m in self.tapset.meta})
         self.plans = [bf.prepare_blur([self.batches[r][i] for i in range(B)], self.tapset, list(range(B)), outs=views[r], **norm_kw)
@@ -421,14 +426,21 @@ def e2e_variant(kind, wl, dev, world, steps):
                 dbatch = ops.u8_to_float(dbatch)
             images = [dbatch[i] for i in range(B)]
             bf.blur_image_list(images, [{"blurring": True}] * B, [dpsf[i] for i in range(B)])
+            # the results of a same-shape batch are [k, :, :, :W] views of ONE row-aligned buffer (blur_batch allocates them
+            # so): convert / copy the whole batch in one go instead of image by image
+            base = images[0]._base
+            whole = base is not None and base.dim() == 4 and all(im._base is base for im in images)
             if kind == "u8":
-                for i in range(B):
-                    ops.float_to_u8(images[i], out=dout[k % n_streams][i])
+                if whole:
+                    ops.float_to_u8(base.view(B * C, H, base.shape[3])[:, :, :W], out=dout[k % n_streams].view(B * C, H, W))
+                else:
+                    for i in range(B):
+                        ops.float_to_u8(images[i], out=dout[k % n_streams][i])
                 hout[k % n_streams].copy_(dout[k % n_streams], non_blocking=True)
+            elif whole:
+                hout[k % n_streams].copy_(base, non_blocking=True)
             else:
                 for i in range(B):
-                    # results are [:, :, :W] views of row-aligned buffers: copy the whole buffer (one plain async memcpy per
-                    # image) instead of letting torch gather the view with an extra device kernel first
                     r = images[i]
                     full = r.as_strided((C, H, r.stride(1)), (r.stride(0), r.stride(1), 1))
                     hout[k % n_streams][i, :, :, :r.stride(1)].copy_(full, non_blocking=True)
@@ -553,15 +565,21 @@ def run_own_arm(args, spec):
     # ---- the other BASELINE configs, measured the same way (N = 1 only: they are records beside the headline, not the metric)
     extra = {}
     if world == 1 and not args.no_extras and spec["name"] == "cfg2":
-        for name in ("cfg3", "cfg5", "cfg2h"):
+        variants = [("cfg3", "cfg3", {}), ("cfg5", "cfg5", {}), ("cfg2h", "cfg2h", {}),
+                    # config 2 again: inputs pitched (rows 16-byte aligned), and through the TMA-staged dense kernel (which the
+                    # default routing reserves for large PSFs) in both input layouts
+                    ("cfg2_pitched_inputs", "cfg2", {"pitched": True}),
+                    ("cfg2_tma_kernel", "cfg2", {"dense_only": True}),
+                    ("cfg2_tma_kernel_pitched_inputs", "cfg2", {"dense_only": True, "pitched": True})]
+        for name, base, kw in variants:
             try:
-                sp = workload_spec(name, None)
-                w2 = Workload(sp, dev, rank)
+                sp = workload_spec(base, None)
+                w2 = Workload(sp, dev, rank, **kw)
                 k2 = max(5, min(K, 40 if name == "cfg3" else 200))
                 reg_o, g_o = time_steps(lambda k: w2.step(k, True), k2, 3, min_ms=40.0)
                 reg_s, _ = time_steps(lambda k: w2.step(k, False), k2, 3, min_ms=30.0)
                 ms_o, ms_s = float(np.median(reg_o)) / k2, float(np.median(reg_s)) / k2
-                extra[name] = {"workload": sp["desc"], "value": w2.B / (ms_o / 1000.0), "unit": "images/s", "steps": k2,
+                extra[name] = {"workload": sp["desc"], "kernels": w2.kernels, "value": w2.B / (ms_o / 1000.0), "unit": "images/s", "steps": k2,
                                "ms_per_step": ms_o, "ms_per_step_ordered": ms_s, "taps": w2.taps,
                                "dtype": "f16 i/o, f32 accumulate" if w2.half else "f32", "cuda_graph": g_o,
                                "roofline": roofline_block(w2, ms_s, ms_o, hbm_peak, peak_src, fp32_tflops)}

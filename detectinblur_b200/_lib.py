@@ -15,6 +15,7 @@ PAD_REFLECT128, PAD_ZERO128, PAD_REPLICATE256 = 0, 1, 2
 EPI_NOISE, EPI_CLAMP, EPI_GAMMA, EPI_NORMALIZE, EPI_PHILOX = 1, 2, 4, 8, 16
 ALGO_AUTO, ALGO_GENERIC, ALGO_TILED = 0, 1, 2
 ALGO_OVERLAP = 0x100
+ALGO_DEVICE_PLAN = 0x200
 
 
 def algo_slot(k):

@@ -82,6 +82,8 @@ class BlurPlan(object):
                     algo |= _lib.algo_slot(ts.launch_seq)
                     if overlap or lo > 0:
                         algo |= _lib.ALGO_OVERLAP
+                    if ts.meta is None and self.algo == _lib.ALGO_AUTO:
+                        algo |= _lib.ALGO_DEVICE_PLAN              # no host copy of the summaries: the device plans
                 _lib.check(_lib.lib.dib_blur_batch(sub, cnt, ctypes.c_void_p(ts.buffer.data_ptr()) if ts is not None else None,
                                                    ts.n_psfs if ts is not None else 0, ts.max_taps if ts is not None else 0,
                                                    ts.meta if ts is not None else None, _DT[self.dtype], algo,
@@ -118,6 +120,13 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
     results = []
     descs = (_lib.Image * n)()
     keep = []
+    # images of one shape and no caller-provided destinations: ONE allocation for all results (views [k, :, :, :W] of an
+    # [n, C, H, W'] buffer with 16-byte-aligned rows), so that a caller can move or convert the whole batch in one go
+    shared_out = None
+    if outs is None and noise is None and n > 1 and all(im.dim() == 3 and im.shape == images[0].shape for im in images):
+        C0, H0, W0 = (int(v) for v in images[0].shape)
+        quad0 = 16 // images[0].element_size()
+        shared_out = torch.empty((n, C0, H0, (W0 + quad0 - 1) // quad0 * quad0), dtype=dtype, device=dev)
     for k, img in enumerate(images):
         psf_ops._require_cuda(img, "image %d" % k)
         if img.dim() != 3:
@@ -134,6 +143,8 @@ def prepare_blur(images, tapset, psf_indices, outs=None, noise=None, noise_sd=No
                 raise ValueError("bad destination tensor for image %d" % k)
         elif noise is not None and noise[k] is not None and tuple(noise[k].shape) == (C, H, W):
             out = torch.empty_like(noise[k], dtype=dtype)            # a pre-drawn noise tensor shares the destination's layout
+        elif shared_out is not None:
+            out = shared_out[k, :, :, :W]
         else:
             quad = 16 // img.element_size()
             out = torch.empty((C, H, (W + quad - 1) // quad * quad), dtype=dtype, device=dev)[:, :, :W]    # 16-byte-aligned rows
@@ -193,6 +204,8 @@ def _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd, clamp, ph
             return False                                   # pass-through images go through the generic kernel's epilogue
         if img.shape[1] <= 64 or img.shape[2] <= 64 or tapset is None or tapset.side > 129:
             return False
+        if tapset.meta is None:
+            return False                                   # device-planned launches: float32 only
         m = tapset.meta[int(psf_indices[k])]
         if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM) or m.prog_group_w != 0:
             return False                                   # in-kernel half I/O is the masked kernel's (small PSFs)

@@ -7,20 +7,31 @@
 
 namespace dib {
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
-                   int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
+                   int io_dtype, uint32_t skip_mask, uint32_t planned_mask, uint64_t seed, uint64_t offset, cudaStream_t st);
 // dense sheared program (blur_tiled.cu): large PSFs, float32 images
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st);
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, const dib_psf_meta* meta_dev,
+                 cudaStream_t st);
 namespace mk {
 // masked program (blur_masked.cu): PSFs whose support fits one chunk, float32 and float16 images
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st);
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, const dib_psf_meta* meta_dev,
+                 cudaStream_t st);
 }  // namespace mk
 
 enum { kNotTiled = 0, kMasked = 1, kDense = 2 };
 
+enum { kPlanned = 3 };      // device-planned: a tiled kernel takes the image if its PSF has a program (decided on the device)
+
 // which tiled kernel, if any, takes this image
-static int tiled_kind(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype) {
+static int tiled_kind(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype, bool device_plan) {
+    if (device_plan) {
+        // the image-side conditions only; float32 only (the in-kernel half path needs the host to know the kernel)
+        if (im.psf_index < 0 || io_dtype != DIB_F32) return kNotTiled;
+        if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return kNotTiled;
+        if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) return kNotTiled;
+        return kPlanned;
+    }
     if (meta_host == nullptr || im.psf_index < 0) return kNotTiled;
     // reflect-101 or zero padding about centre 63; tiny images (the reference's own zero-padding case) stay on the generic kernel
     if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return kNotTiled;
@@ -52,7 +63,8 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     DIB_CHECK_ARG(io_dtype == DIB_F32 || io_dtype == DIB_F16, "dib_blur_batch: io_dtype must be DIB_F32 or DIB_F16");
     const bool overlap_prev = (algo & DIB_ALGO_OVERLAP) != 0;
     const int sched_slot = (algo >> 12) & (kSchedSlots - 1);
-    DIB_CHECK_ARG((algo & ~(0xff | DIB_ALGO_OVERLAP | DIB_ALGO_SLOT(3))) == 0, "dib_blur_batch: unknown algo flags 0x%x", algo);
+    const bool device_plan = (algo & DIB_ALGO_DEVICE_PLAN) != 0;
+    DIB_CHECK_ARG((algo & ~(0xff | DIB_ALGO_OVERLAP | DIB_ALGO_DEVICE_PLAN | DIB_ALGO_SLOT(3))) == 0, "dib_blur_batch: unknown algo flags 0x%x", algo);
     algo &= 0xff;
     DIB_CHECK_ARG(algo == DIB_ALGO_AUTO || algo == DIB_ALGO_GENERIC || algo == DIB_ALGO_TILED, "dib_blur_batch: unknown algo %d", algo);
     if (n_images == 0) return DIB_OK;
@@ -89,10 +101,15 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
     int order[2][DIB_MAX_BATCH];
     int n_kind[2] = {0, 0};
     uint32_t tiled_mask = 0;
+    uint32_t planned_mask = 0;
     if (algo != DIB_ALGO_GENERIC) {
         for (int k = 0; k < n_images; ++k) {
-            const int kind = tiled_kind(images[k], meta_host, io_dtype);
-            if (kind != kNotTiled) {
+            const int kind = tiled_kind(images[k], meta_host, io_dtype, device_plan);
+            if (kind == kPlanned) {             // listed for both tiled kernels; each takes its own on the device
+                order[0][n_kind[0]++] = k;
+                order[1][n_kind[1]++] = k;
+                planned_mask |= 1u << k;
+            } else if (kind != kNotTiled) {
                 order[kind - 1][n_kind[kind - 1]++] = k;
                 tiled_mask |= 1u << k;
             } else if (algo == DIB_ALGO_TILED) {
@@ -103,7 +120,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
             }
         }
         // insertion sort by tap count, descending (stable): the dynamic scheduler hands out long tiles first
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < 2 && !device_plan; ++q) {
             for (int a = 1; a < n_kind[q]; ++a) {
                 const int v = order[q][a];
                 const int cv = meta_host[images[v].psf_index].count;
@@ -116,22 +133,24 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
             }
         }
     }
-    const int n_sel = n_kind[0] + n_kind[1];
+    const dib_psf_meta* plan_meta = device_plan ? meta_dev : nullptr;
+    const int n_sel = device_plan ? 0 : n_kind[0] + n_kind[1];
     int nl = 0;
     if (n_kind[0] > 0) {
-        const int rc = mk::launch_tiled(images, order[0], n_kind[0], meta_host, prog, sched, philox_seed, philox_offset, io_dtype, overlap_prev, st);
+        const int rc = mk::launch_tiled(images, order[0], n_kind[0], meta_host, prog, sched, philox_seed, philox_offset, io_dtype, overlap_prev,
+                                        plan_meta, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }
     if (n_kind[1] > 0) {
         // its own scheduler words: the two tiled launches of one call may be co-resident
         const int rc = launch_tiled(images, order[1], n_kind[1], meta_host, prog, sched + kSchedSlots, philox_seed, philox_offset, io_dtype,
-                                    overlap_prev, st);
+                                    overlap_prev, plan_meta, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }
     if (n_sel < n_images) {
-        const int rc = launch_generic(images, n_images, taps, meta_dev, max_taps, io_dtype, tiled_mask, philox_seed, philox_offset, st);
+        const int rc = launch_generic(images, n_images, taps, meta_dev, max_taps, io_dtype, tiled_mask, planned_mask, philox_seed, philox_offset, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

@@ -19,6 +19,8 @@ struct GenericParams {
     int n_images;
     uint64_t philox_seed, philox_offset;
     uint32_t skip_mask;      // bit i set: image i is handled by another kernel
+    uint32_t planned_mask;   // DIB_ALGO_DEVICE_PLAN: bit i set: a tiled kernel takes image i if its PSF has a program (decided here
+                             // from the device-side summary, as the tiled kernels do)
 };
 
 template <typename T>
@@ -48,6 +50,7 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
     const int n = blockIdx.y;
     if ((p.skip_mask >> n) & 1u) return;
     const dib_image& im = p.img[n];
+    if (((p.planned_mask >> n) & 1u) && im.psf_index >= 0 && psf_program_kind(p.meta[im.psf_index]) != 0) return;
     const int64_t pix = (int64_t)blockIdx.x * kGenericThreads + threadIdx.x;
     if (pix >= (int64_t)im.H * im.W) return;
     const int i = (int)(pix / im.W), j = (int)(pix - (int64_t)i * im.W);
@@ -113,7 +116,7 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
 
 // Launch helper used by dib_blur_batch (blur_api.cu).
 int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, const dib_psf_meta* meta, int max_taps,
-                   int io_dtype, uint32_t skip_mask, uint64_t seed, uint64_t offset, cudaStream_t st) {
+                   int io_dtype, uint32_t skip_mask, uint32_t planned_mask, uint64_t seed, uint64_t offset, cudaStream_t st) {
     GenericParams p;
     int64_t max_pix = 0;
     for (int k = 0; k < n_images; ++k) {
@@ -131,6 +134,7 @@ int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, c
     p.philox_seed = seed;
     p.philox_offset = offset;
     p.skip_mask = skip_mask;
+    p.planned_mask = planned_mask;
     dim3 grid((unsigned)((max_pix + kGenericThreads - 1) / kGenericThreads), (unsigned)n_images);
     if (io_dtype == DIB_F32)
         blur_generic_kernel<float><<<grid, kGenericThreads, 0, st>>>(p);

@@ -45,6 +45,7 @@ namespace mk {
 // registers, allows only 8 compute warps and measured 5 % slower; kR = 2 with 16 compute warps (104 registers) has
 // more warps to hide latency with but a third fewer FMAs per window load and measured 7 % slower.  (Its first build
 // hung: setmaxnreg.inc asked for more registers than the CTA's launch-time allocation holds -- see kLaunchRegs.)
+constexpr int kDevicePlanShear = 0;      // this kernel's programs are not sheared
 constexpr int kR = 3;                   // row pairs per thread
 constexpr int kRows = 2 * kR;               // output rows per thread (= rotation period of the register window)
 constexpr int kCC = 7;                      // output columns per thread (odd: conflict-free lane stride)
@@ -108,7 +109,32 @@ struct TiledParams {
     uint64_t philox_seed, philox_offset;
     SchedWords* sched;            // dynamic tile scheduler (tap set buffer): tiles are handed out in index order
     int overlap_prev;             // DIB_ALGO_OVERLAP: do not wait for the grid launched before this one
+    const dib_psf_meta* meta_dev; // DIB_ALGO_DEVICE_PLAN: per-PSF summaries on the device decide which images are this kernel's
 };
+
+// ---------------------------------------------------------------- optional timeline trace (kernel experiments only)
+#ifdef DIB_TRACE
+constexpr int kTracePerWarp = 4096;
+__device__ unsigned long long g_trace[16 * kTracePerWarp];
+__device__ unsigned int g_trace_n[16];
+__device__ __forceinline__ void trace_event(int ev, int arg) {
+    __shared__ unsigned int pos[16];
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        unsigned int i = pos[w];
+        if (i >= (unsigned)kTracePerWarp) i = 0;
+        i = (ev == 63) ? 0 : i;
+        if (i < (unsigned)kTracePerWarp - 1) {
+            g_trace[w * kTracePerWarp + i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(arg & 0xfff) << 12) | (w << 6) | (unsigned)ev;
+            pos[w] = i + 1;
+            g_trace_n[w] = i + 1;
+        }
+    }
+}
+#define DIB_TRACE_EVENT(ev, arg) trace_event(ev, arg)
+#else
+#define DIB_TRACE_EVENT(ev, arg)
+#endif
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,6 +247,7 @@ static_assert(sizeof(StageHdr) <= kHdrBytes, "stage header too large");
 struct Stage {
     int tile;       // global tile index, -1: none
     int chunk;
+    int nchunks;    // chunks of the image's program; 0: the image belongs to another kernel (device-planned launches)
     int img, ch, i0, j0;
     ChunkRec rec;
 };
@@ -254,6 +281,16 @@ __device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stag
     const int ty = rem / im.tiles_x;
     st.i0 = ty * kTH;
     st.j0 = (rem - ty * im.tiles_x) * kTW;
+    st.nchunks = im.nchunks;
+    if (p.meta_dev != nullptr) {          // planned on the device: the program's kind and length come from the PSF summary
+        const dib_psf_meta* m = p.meta_dev + im.psf_index;
+        const int4 a = __ldg(reinterpret_cast<const int4*>(m));            // count | ymin ymax | xmin xmax | sum
+        const int4 b = __ldg(reinterpret_cast<const int4*>(m) + 1);        // support | prog_chunks | prog_steps | flags
+        const int2 c = __ldg(reinterpret_cast<const int2*>(m) + 4);        // prog_segs | prog_group_w, prog_shear
+        dib_psf_meta mm;
+        mm.count = a.x; mm.prog_chunks = b.y; mm.flags = b.w; mm.prog_group_w = (int16_t)(c.y & 0xffff);
+        st.nchunks = psf_program_kind(mm) == 1 ? mm.prog_chunks : 0;
+    }
 }
 
 __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img, int chunk) {
@@ -292,14 +329,16 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
         nx.tile = -1;
         return;
     }
-    if (cur.chunk + 1 < p.img[cur.img].nchunks) {
+    if (cur.chunk + 1 < cur.nchunks) {
         nx = cur;
         nx.chunk = cur.chunk + 1;
     } else {
-        nx.tile = fetch_tile(p, slots, nfetch, pt);
-        if (nx.tile < 0) return;
-        nx.chunk = 0;
-        decode_tile(p, nx.tile, nx);
+        do {        // device-planned launches: tiles of images that belong to another kernel are skipped
+            nx.tile = fetch_tile(p, slots, nfetch, pt);
+            if (nx.tile < 0) return;
+            nx.chunk = 0;
+            decode_tile(p, nx.tile, nx);
+        } while (nx.nchunks == 0);
     }
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
 }
@@ -346,7 +385,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         StageHdr h;
         h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
         h.first_chunk = (st.chunk == 0);
-        h.last_chunk = (st.chunk + 1 == im.nchunks);
+        h.last_chunk = (st.chunk + 1 == st.nchunks);
         h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
         *sm.hdr = h;
     }
@@ -408,7 +447,7 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
         StageHdr h;
         h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
         h.first_chunk = (st.chunk == 0);
-        h.last_chunk = (st.chunk + 1 == im.nchunks);
+        h.last_chunk = (st.chunk + 1 == st.nchunks);
         h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.wsteps = st.rec.wsteps;
         *sm.hdr = h;
     }
@@ -648,6 +687,7 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         const int sg = reverse ? nseg - 1 - sgi : sgi;
         int raw0, raw1;         // SegRec {dx0, dy0 | nsteps, woff} as two words
         lds_entry(aux + 8u * (uint32_t)sg, reinterpret_cast<float&>(raw0), raw1);
+        DIB_TRACE_EVENT(2, raw1 & 0xffff);
         const int seg_dx0 = (int)(short)(raw0 & 0xffff), seg_dy0 = raw0 >> 16;
         const int nsteps = (int)(short)(raw1 & 0xffff), seg_woff = raw1 >> 16;
         const int colbase = wcol * kWarpW + kCC * lane - seg_dx0 - (kGroupW - 1) + dx_hi;
@@ -660,9 +700,11 @@ __device__ __forceinline__ void compute_chunk(float2 (&acc)[kR][kCC], uint32_t s
         fill_window<0>(win, tile_cb, rowtab, sr0);
         int ro_next = 0;
         int s = 0;
+        DIB_TRACE_EVENT(6, sg);
 #pragma unroll 1
         while (SweepRound<0>::run(acc, win, tile_cb, rowtab, sr0, s, nsteps, wp, ro_next, wv)) {
         }
+        DIB_TRACE_EVENT(3, sg);
     }
 }
 
@@ -909,6 +951,7 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
     // (and flush) before touching global memory.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
+    DIB_TRACE_EVENT(63, 0);
 
     if (threadIdx.x == 0) {
         // float: per producer thread one arrive.expect_tx + one cp.async arrive; half: one plain arrive after widening
@@ -930,12 +973,13 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         const int pt = threadIdx.x;
         Stage cur, nxt;
         int nfetch = 0;
-        cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
         cur.chunk = 0;
-        if (cur.tile >= 0) {
+        do {        // (device-planned launches skip the tiles of images that belong to another kernel)
+            cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
+            if (cur.tile < 0) break;
             decode_tile(p, cur.tile, cur);
-            cur.rec = load_chunk_rec(p, cur.img, 0);
-        }
+        } while (cur.nchunks == 0);
+        if (cur.tile >= 0) cur.rec = load_chunk_rec(p, cur.img, 0);
         for (int n = 0;; ++n) {
             const int b = n & 1;
             next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the issue below
@@ -979,7 +1023,9 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
         for (int n = 0;; ++n) {
             const int b = n & 1;
             const StageSmem sm = stage_smem(smem, b);
+            DIB_TRACE_EVENT(0, n);
             mbar_wait(&full[b], (n >> 1) & 1);
+            DIB_TRACE_EVENT(1, n);
             StageHdr h;
             {   // explicit vector loads keep the header in registers
                 const int4 a = reinterpret_cast<const int4*>(sm.hdr)[0], b4 = reinterpret_cast<const int4*>(sm.hdr)[1];
@@ -1001,7 +1047,9 @@ __global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_co
             if (active) compute_chunk(acc, smem_u32(sm.hdr), h.nseg, h.dy_hi, h.dx_hi, wrow, wcol);
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
+            DIB_TRACE_EVENT(4, n);
             if (h.last_chunk && active) store_rows<kEpi, kHalf>(p, im, h.ch, row0, col0, acc, obuf);
+            DIB_TRACE_EVENT(5, n);
         }
     }
 }
@@ -1014,7 +1062,8 @@ int tiled_tile_counts(int H, int W, int* tiles_y, int* tiles_x) {
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st) {
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, const dib_psf_meta* meta_dev,
+                 cudaStream_t st) {
     static thread_local int sm_count = 0;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
@@ -1033,7 +1082,12 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     bool any_epi = false, any_general = false;
     for (int k = 0; k < n_sel; ++k) {   // `order` lists the images heaviest PSF first: tiles are handed out in this order
         const dib_image& im = images[order[k]];
-        const dib_psf_meta& m = meta_host[im.psf_index];
+        // planned on the device (meta_dev): no host copy of the summaries -- the kernel reads chunk counts itself, tiles are
+        // counted for the widest shear, and every image is listed (each kernel skips the images of the other)
+        dib_psf_meta planned = {};
+        planned.prog_chunks = -1;
+        planned.prog_shear = (int16_t)kDevicePlanShear;
+        const dib_psf_meta& m = meta_dev != nullptr ? planned : meta_host[im.psf_index];
         TiledImage& t = p.img[k];
         t.src = im.src;
         t.dst = im.dst;
@@ -1054,7 +1108,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
         // A PSF whose program is one chunk: taps.cu builds that chunk from the support's bounding box alone (first group at
         // xmin, rows ymin .. ymax, data right after the chunk table), so the record is reproduced here from the host summary.
         t.rec0_valid = 0;
-        if (m.prog_chunks == 1) {
+        if (meta_dev == nullptr && m.prog_chunks == 1) {
             const int centre = 63;
             const int g_last = (m.xmax - m.xmin) / kGroupW;
             t.rec0.dy_lo = (int16_t)(m.ymin - centre);
@@ -1085,7 +1139,10 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_seed = seed;
     p.philox_offset = offset;
     p.sched = sched;
-    p.overlap_prev = overlap_prev ? 1 : 0;
+    p.meta_dev = meta_dev;
+    // a grid smaller than the machine could be co-resident with many successors (more than the scheduler slots cover):
+    // it always orders itself after its predecessor
+    p.overlap_prev = (overlap_prev && total >= sm_count) ? 1 : 0;
     const int grid = total < sm_count ? total : sm_count;     // persistent: one CTA per SM
     // launched with the programmatic-stream-serialization attribute: the kernel itself decides (griddepcontrol.wait)
     // whether it orders itself after the previous launch
@@ -1121,3 +1178,20 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
 
 }  // namespace mk
 }  // namespace dib
+
+#ifdef DIB_TRACE
+extern "C" __attribute__((visibility("default"))) int dib_debug_trace_masked(unsigned long long* out, int max_events) {
+    unsigned int n[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(n, dib::mk::g_trace_n, sizeof(n));
+    int total = 0;
+    for (int w = 0; w < 16; ++w) {
+        int c = (int)n[w];
+        if (c > dib::mk::kTracePerWarp) c = dib::mk::kTracePerWarp;
+        if (total + c > max_events) c = max_events - total;
+        if (c > 0) cudaMemcpyFromSymbol(out + total, dib::mk::g_trace, sizeof(unsigned long long) * c, sizeof(unsigned long long) * w * dib::mk::kTracePerWarp);
+        total += c > 0 ? c : 0;
+    }
+    return total;
+}
+#endif

@@ -41,6 +41,7 @@ namespace dib {
 #ifndef DIB_PRODUCER_REGS
 #define DIB_PRODUCER_REGS 88
 #endif
+constexpr int kDevicePlanShear = kShearMax;  // device-planned launches count tiles for the widest shear
 constexpr int kProducerWarps = 4;           // one warpgroup: a thread issues at most one TMA box per stage
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
@@ -89,6 +90,7 @@ struct TiledParams {
     uint64_t philox_seed, philox_offset;
     SchedWords* sched;            // dynamic tile scheduler (tap set buffer): tiles are handed out in index order
     int overlap_prev;             // DIB_ALGO_OVERLAP: do not wait for the grid launched before this one
+    const dib_psf_meta* meta_dev; // DIB_ALGO_DEVICE_PLAN: per-PSF summaries on the device decide which images are this kernel's
 };
 
 // ---------------------------------------------------------------- optional timeline trace (kernel experiments only)
@@ -234,6 +236,7 @@ static_assert(sizeof(StageHdr) <= kStageHdrBytes, "stage header too large");
 struct Stage {
     int tile;       // global tile index, -1: none
     int chunk;
+    int nchunks;    // chunks of the image's program; 0: the image belongs to another kernel (device-planned launches)
     int img, ch, i0, j0;
     ChunkRec rec;
 };
@@ -252,6 +255,16 @@ __device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stag
     const int ty = rem / im.tiles_x;
     st.i0 = ty * kTH;
     st.j0 = (rem - ty * im.tiles_x) * kTW;
+    st.nchunks = im.nchunks;
+    if (p.meta_dev != nullptr) {          // planned on the device: the program's kind and length come from the PSF summary
+        const dib_psf_meta* m = p.meta_dev + im.psf_index;
+        const int4 a = __ldg(reinterpret_cast<const int4*>(m));            // count | ymin ymax | xmin xmax | sum
+        const int4 b = __ldg(reinterpret_cast<const int4*>(m) + 1);        // support | prog_chunks | prog_steps | flags
+        const int2 c = __ldg(reinterpret_cast<const int2*>(m) + 4);        // prog_segs | prog_group_w, prog_shear
+        dib_psf_meta mm;
+        mm.count = a.x; mm.prog_chunks = b.y; mm.flags = b.w; mm.prog_group_w = (int16_t)(c.y & 0xffff);
+        st.nchunks = psf_program_kind(mm) == 2 ? mm.prog_chunks : 0;
+    }
 }
 
 __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img, int chunk) {
@@ -292,14 +305,16 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
         nx.tile = -1;
         return;
     }
-    if (cur.chunk + 1 < p.img[cur.img].nchunks) {
+    if (cur.chunk + 1 < cur.nchunks) {
         nx = cur;
         nx.chunk = cur.chunk + 1;
     } else {
-        nx.tile = fetch_tile(p, slots, nfetch, pt);
-        if (nx.tile < 0) return;
-        nx.chunk = 0;
-        decode_tile(p, nx.tile, nx);
+        do {        // device-planned launches: tiles of images that belong to another kernel are skipped
+            nx.tile = fetch_tile(p, slots, nfetch, pt);
+            if (nx.tile < 0) return;
+            nx.chunk = 0;
+            decode_tile(p, nx.tile, nx);
+        } while (nx.nchunks == 0);
     }
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
 }
@@ -336,7 +351,7 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         StageHdr h;
         h.tile = st.tile; h.img = st.img; h.ch = st.ch; h.i0 = st.i0; h.j0 = st.j0;
         h.first_chunk = (st.chunk == 0);
-        h.last_chunk = (st.chunk + 1 == im.nchunks);
+        h.last_chunk = (st.chunk + 1 == st.nchunks);
         h.dy_hi = st.rec.dy_hi; h.dx_hi = st.rec.dx_hi; h.nseg = st.rec.nseg; h.group_w = st.rec.group_w; h.shear = st.rec.shear;
         h.skew0 = g.skew0; h.dskew = g.dskew;
         StageHdr* hp = reinterpret_cast<StageHdr*>(__cvta_shared_to_generic(sbase));
@@ -817,10 +832,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) blur_tiled_kernel(const 
         const int pt = threadIdx.x;
         Stage cur, nxt;
         int nfetch = 0;
-        cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
         cur.chunk = 0;
-        if (cur.tile >= 0) {
+        do {        // (device-planned launches skip the tiles of images that belong to another kernel)
+            cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
+            if (cur.tile < 0) break;
             decode_tile(p, cur.tile, cur);
+        } while (cur.nchunks == 0);
+        if (cur.tile >= 0) {
             cur.rec = load_chunk_rec(p, cur.img, 0);
             issue_stage(p, cur, stage_base(smem_base, 0), &landed[0], pt);
         }
@@ -943,7 +961,8 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib_psf_meta* meta_host, const uint8_t* prog,
-                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, cudaStream_t st) {
+                 SchedWords* sched, uint64_t seed, uint64_t offset, int io_dtype, bool overlap_prev, const dib_psf_meta* meta_dev,
+                 cudaStream_t st) {
     static thread_local int sm_count = 0;
     static thread_local int attr_set_dev = -1;
     int dev = 0;
@@ -969,7 +988,12 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     bool any_epi = false, any_general = false;
     for (int k = 0; k < n_sel; ++k) {   // `order` lists the images heaviest PSF first: tiles are handed out in this order
         const dib_image& im = images[order[k]];
-        const dib_psf_meta& m = meta_host[im.psf_index];
+        // planned on the device (meta_dev): no host copy of the summaries -- the kernel reads chunk counts itself, tiles are
+        // counted for the widest shear, and every image is listed (each kernel skips the images of the other)
+        dib_psf_meta planned = {};
+        planned.prog_chunks = -1;
+        planned.prog_shear = (int16_t)kDevicePlanShear;
+        const dib_psf_meta& m = meta_dev != nullptr ? planned : meta_host[im.psf_index];
         TiledImage& t = p.img[k];
         t.src = im.src;
         t.dst = im.dst;
@@ -1030,6 +1054,7 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     p.philox_seed = seed;
     p.philox_offset = offset;
     p.sched = sched;
+    p.meta_dev = meta_dev;
     // Overlapped launches share SMs only while the earlier grid drains: with one CTA per SM and a full grid at most two
     // launches are ever co-resident, which the four scheduler slots cover.  A grid smaller than the machine could be
     // co-resident with many successors, so it always orders itself after its predecessor.

@@ -127,6 +127,13 @@ struct SchedWords {
 constexpr int kSchedSlots = 4;      // launches that may overlap (DIB_ALGO_OVERLAP) rotate through these (256 bytes are reserved)
 
 
+// Device-side launch planning (DIB_ALGO_DEVICE_PLAN): which kernel takes a PSF is read from the tap set's summaries on the
+// device instead of a host copy of them.  0: no tiled program; kMasked / kDense as in blur_api.cu.
+__host__ __device__ inline int psf_program_kind(const dib_psf_meta& m) {
+    if (m.count <= 0 || m.prog_chunks <= 0 || (m.flags & (DIB_META_NO_PROGRAM | DIB_META_TRUNCATED))) return 0;
+    return m.prog_group_w == 0 ? 1 : 2;
+}
+
 inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 inline dib_tapset_layout tapset_layout(int n, int max_taps) {

@@ -293,7 +293,7 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
 
 template <typename T, bool kStaged>
 __global__ void __launch_bounds__(kCompactThreads)
-compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int normalize, dib_psf_meta* __restrict__ meta,
+compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int flags_in, dib_psf_meta* __restrict__ meta,
                     dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog, SchedWords* __restrict__ sched) {
     __shared__ double sh_d[kCompactThreads / 32];
     __shared__ long long sh_ll[kCompactThreads / 32];
@@ -309,6 +309,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ unsigned long long sh_cost[kNumCand];
     __shared__ int sh_nchunks, sh_nsegs, sh_total_steps, sh_choice;
 
+    const int normalize = flags_in & DIB_COMPACT_NORMALIZE;
     const int n = blockIdx.x;
     if (n == 0 && threadIdx.x == 0) {
         for (int k = 0; k < 2 * kSchedSlots; ++k) {      // masked kernel: slots 0-3, dense kernel: slots 4-7
@@ -427,7 +428,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __syncthreads();
     // A PSF whose support fits one chunk of the masked kernel's program (every low-exposure PSF) takes that kernel: it is
     // the faster one there; everything else gets the dense sheared program.
-    const bool small_psf = want_prog && ymax - ymin <= mk::kChunkHaloRows && xmax - xmin < mk::kChunkGroups * mk::kGroupW;
+    const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY) && ymax - ymin <= mk::kChunkHaloRows &&
+                           xmax - xmin < mk::kChunkGroups * mk::kGroupW;
     int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
     if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
     if (want_prog && !(small_psf && mk_chunks == 1)) {
@@ -727,6 +729,7 @@ extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int
     DIB_CHECK_ARG(psf_stride >= (int64_t)side * side, "dib_compact_taps: psf_stride %lld smaller than one PSF",
                   (long long)psf_stride);
     DIB_CHECK_ARG(max_taps > 0, "dib_compact_taps: max_taps must be > 0");
+    DIB_CHECK_ARG((normalize & ~(DIB_COMPACT_NORMALIZE | DIB_COMPACT_DENSE_ONLY)) == 0, "dib_compact_taps: unknown flag bits 0x%x", normalize);
     DIB_CHECK_ARG(psf_dtype == DIB_F32 || psf_dtype == DIB_F16, "dib_compact_taps: PSF dtype must be DIB_F32 or DIB_F16");
     const dib_tapset_layout L = tapset_layout(n_psfs, max_taps);
     uint8_t* base = static_cast<uint8_t*>(tapset);

@@ -10,6 +10,7 @@ Reference code these stand in for:
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -41,11 +42,19 @@ class TapSet(object):
 
     @property
     def counts(self):
-        return [m.count for m in self.meta]
+        return [m.count for m in self._host_meta()]
+
+    def _host_meta(self):
+        """The per-PSF summaries on the host; a tap set compacted with ``sync=False`` fetches them on first use."""
+        if self.meta is None:
+            n = self.n_psfs
+            raw = self.buffer[self.layout.meta_offset:self.layout.meta_offset + n * ctypes.sizeof(_lib.PsfMeta)].cpu().numpy().tobytes()
+            self.meta = (_lib.PsfMeta * n).from_buffer_copy(raw)
+        return self.meta
 
     def taps(self, index):
         """(ys, xs, weights) of PSF ``index`` as numpy arrays, in accumulation order (copies device -> host)."""
-        n = min(self.meta[index].count, self.max_taps)
+        n = min(self._host_meta()[index].count, self.max_taps)
         off = self.layout.taps_offset + index * self.max_taps * 8
         raw = self.buffer[off:off + n * 8].cpu().numpy().tobytes()
         rec = np.frombuffer(raw, dtype=np.dtype([("y", "<i2"), ("x", "<i2"), ("w", "<f4")]))
@@ -53,12 +62,12 @@ class TapSet(object):
 
     def tap_extents(self, index, centre=63):
         """(left, top, right, bottom) tap offsets relative to the centre -- utils.py:375-379."""
-        m = self.meta[index]
+        m = self._host_meta()[index]
         return m.xmin - centre, m.ymin - centre, m.xmax - centre, m.ymax - centre
 
     def psf_pca(self, index):
         """(theta_rad, scale_factor_lambda1, scale_factor_lambda2) from the support moments -- transforms.py:366-385."""
-        m = self.meta[index]
+        m = self._host_meta()[index]
         n = float(m.support)
         mean_y, mean_x = m.sy / n, m.sx / n
         var_y = m.syy / n - mean_y * mean_y
@@ -77,14 +86,21 @@ class TapSet(object):
         return theta, s1, s2
 
 
-def compact_taps(psfs, normalize, max_taps=1024):
+def compact_taps(psfs, normalize, max_taps=1024, dense_only=None, sync=True):
     """Compact a batch of dense PSFs ([n, k, k] or [k, k] CUDA tensor, float32 / float16) into a TapSet.
 
     One launch for the batch, then one small device->host copy of the per-PSF summaries (counts, extents,
     program sizes) that the blur launcher plans with.  ``max_taps`` sizes the per-PSF tap list (what the exact-order
     kernel walks); a PSF with more nonzero cells -- e.g. one widened by ``--dilate_psf`` (transforms.py:338-342) -- makes the
     call repeat itself once with a list that holds the largest count, as the reference simply loops over more taps.
+    ``dense_only`` (default: the DIB_DENSE_ONLY environment variable) gives small PSFs the dense sheared program too, i.e.
+    routes every image to the TMA-staged tiled kernel -- for measurements; the default picks the faster kernel per PSF.
+    ``sync=False`` skips the read-back of the summaries: the TapSet then has ``meta = None`` and ``blur_batch`` plans the launch
+    on the device (DIB_ALGO_DEVICE_PLAN) -- nothing between the PSFs' upload and the blurred images waits for the host, so the
+    chain can be captured in a CUDA graph.  ``max_taps`` must then hold the largest PSF (4096 covers any 128 x 128 motion PSF).
     """
+    if dense_only is None:
+        dense_only = os.environ.get("DIB_DENSE_ONLY", "0") not in ("0", "", "false", "False")
     _require_cuda(psfs, "psfs")
     if psfs.dim() == 2:
         psfs = psfs.unsqueeze(0)
@@ -98,15 +114,17 @@ def compact_taps(psfs, normalize, max_taps=1024):
     buf = torch.empty(lay.total_bytes, dtype=torch.uint8, device=psfs.device)
     with torch.cuda.device(psfs.device):
         _lib.check(_lib.lib.dib_compact_taps(ctypes.c_void_p(psfs.data_ptr()), _TORCH_TO_DIB[psfs.dtype], n, side,
-                                             side * side, 1 if normalize else 0, ctypes.c_void_p(buf.data_ptr()),
+                                             side * side, (1 if normalize else 0) | (2 if dense_only else 0), ctypes.c_void_p(buf.data_ptr()),
                                              int(max_taps), _stream_ptr(psfs.device)))
+        if not sync:
+            return TapSet(buf, lay, n, int(max_taps), side, None)
         meta_bytes = buf[lay.meta_offset:lay.meta_offset + n * ctypes.sizeof(_lib.PsfMeta)].cpu().numpy().tobytes()
     meta = (_lib.PsfMeta * n).from_buffer_copy(meta_bytes)
     worst = max(m.count for m in meta)
     if worst > max_taps:
         if worst > side * side:
             raise _lib.DibError(_lib.ERR_CAPACITY, "PSF tap count %d exceeds the PSF's %d cells" % (worst, side * side))
-        return compact_taps(psfs, normalize, max_taps=1 << (worst - 1).bit_length())
+        return compact_taps(psfs, normalize, max_taps=1 << (worst - 1).bit_length(), dense_only=dense_only)
     return TapSet(buf, lay, n, int(max_taps), side, meta)
 
 

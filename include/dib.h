@@ -126,6 +126,13 @@ typedef struct dib_image {
  * grid.  Launches that may overlap and share a tap set must use different scheduler slots: DIB_ALGO_SLOT(k), k = a launch
  * counter modulo 4.  Without the flag a launch is ordered after everything before it on the stream, as usual. */
 #define DIB_ALGO_OVERLAP 0x100
+/* DIB_ALGO_DEVICE_PLAN: plan the launch on the device.  No host copy of the per-PSF summaries is needed (meta_host may be
+ * NULL), so nothing has to be read back between dib_compact_taps and dib_blur_batch and the whole chain rasterise -> compact
+ * -> blur can be enqueued without a host synchronisation (and captured in a CUDA graph): both tiled kernels and the exact-
+ * order kernel are launched and each takes, from the summaries in the tap set, the images that are its own.  float32
+ * images; max_taps must hold every PSF of the tap set (a truncated PSF falls to the exact-order kernel with its first
+ * max_taps taps -- size the list for the worst case, 4096 covers every 128 x 128 motion PSF). */
+#define DIB_ALGO_DEVICE_PLAN 0x200
 #define DIB_ALGO_SLOT(k) (((k) & 3) << 12)
 
 DIB_API int dib_abi_version(void);
@@ -137,13 +144,17 @@ DIB_API int dib_device_info(int* sm_count, int* cc);
  * Tap compaction.  Replaces `psf_GPU/psf_GPU.sum()` (blur_functions.py:98) and `psf_GPU.nonzero()` with the
  * two per-tap device->host index reads of the loop (blur_functions.py:63-67), for a whole batch in one launch.
  *   psfs        n dense side x side PSFs, `psf_stride` elements apart, dtype DIB_F32 or DIB_F16
- *   normalize   1: divide by the PSF's sum in the PSF dtype (blur_image_list); 0: PSF already normalised (manual_blur)
+ *   normalize   flags: DIB_COMPACT_NORMALIZE (1) divides by the PSF's sum in the PSF dtype (blur_image_list; without it the PSF
+ *               is taken as already normalised, manual_blur); DIB_COMPACT_DENSE_ONLY (2) gives every PSF the dense sheared
+ *               program of the TMA-staged tiled kernel, also the small ones that would otherwise get the masked kernel's
  *   tapset      caller-owned device buffer of dib_tapset_layout(...).total_bytes
  * Taps come out in row-major order; with normalize = 0 the weights are the PSF's own values, with normalize = 1 the sum is
  * accumulated in fp64 and rounded once to the PSF dtype -- torch's result for every PSF on the fp16 grid that sums to at most
  * 1 (all stored / generated PSFs); a general fp32 PSF can differ from torch's reduction tree by one ulp of the sum (the
  * wrapper's exact mode normalises such PSFs with torch and passes normalize = 0).  meta carries counts, extents, PCA moments.
  */
+#define DIB_COMPACT_NORMALIZE 1
+#define DIB_COMPACT_DENSE_ONLY 2
 DIB_API int dib_tapset_layout_for(int n_psfs, int max_taps, dib_tapset_layout* out);
 DIB_API int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int side, int64_t psf_stride, int normalize,
                      void* tapset, int max_taps, void* stream);

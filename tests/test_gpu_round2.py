@@ -211,3 +211,63 @@ def test_u8_conversions(dib):
     assert torch.equal(ops.float_to_u8(x).cpu(), want) and torch.equal(ops.float_to_u8(pitched).cpu(), want)
     with pytest.raises(TypeError):
         ops.u8_to_float(x)
+
+
+def test_device_planned_launch_matches_host_planned(dib):
+    """compact_taps(sync=False) + blur_batch: no host copy of the PSF summaries, the launch is planned on the device
+    (DIB_ALGO_DEVICE_PLAN): both tiled kernels and the exact-order kernel are launched and each takes its own images.
+    Same bits as the host-planned call, for a batch that exercises every route; and the chain can be captured in a CUDA
+    graph and replayed."""
+    bf, ops = dib
+    np.random.seed(10)
+    small16, _ = po.stored_psf(0.005, 1 / 10, np.random)
+    big16, _ = po.stored_psf(0.00005, 1.0, np.random)
+    edge = np.zeros((128, 128), np.float32)
+    edge[127, 60] = 0.5
+    edge[63, 63] = 0.5                                        # a tap on PSF row 127: no tiled program, exact-order kernel
+    psfs = _cuda(np.stack([po.crop128(small16).astype(np.float32), po.crop128(big16).astype(np.float32), edge]))
+    g = torch.Generator().manual_seed(4)
+    imgs = [torch.rand((3, 210, 700), generator=g).cuda(), torch.rand((3, 333, 500), generator=g).cuda(),
+            torch.rand((3, 100, 130), generator=g).cuda(), torch.rand((3, 40, 50), generator=g).cuda(),
+            torch.rand((3, 90, 70), generator=g).cuda(), torch.rand((2, 128, 449), generator=g).cuda()]
+    idx = [0, 1, 2, 0, -1, 1]
+    ts_host = ops.compact_taps(psfs, normalize=True, max_taps=4096)
+    want = bf.blur_batch(imgs, ts_host, idx)
+    ts_dev = ops.compact_taps(psfs, normalize=True, max_taps=4096, sync=False)
+    assert ts_dev.meta is None
+    l0 = bf.launch_count()
+    got = bf.blur_batch(imgs, ts_dev, idx)
+    assert bf.launch_count() - l0 == 3                        # masked + dense + exact-order, each skipping what is not its own
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # the whole chain under a CUDA graph: rasterise (device trajectories) -> compact -> blur, replayed twice
+    traj = ops.generate_trajectories(2, [0.005, 0.00005], 3, "cuda")
+    fr = [1 / 5, 1.0]
+    outs = [torch.zeros_like(imgs[0]), torch.zeros_like(imgs[1])]
+
+    def chain():
+        p = ops.rasterize_psfs(traj, fr, "cuda", dtype=torch.float32)
+        t = ops.compact_taps(p, normalize=True, max_taps=4096, sync=False)
+        bf.blur_batch(imgs[:2], t, [0, 1], outs=outs)
+        return t
+
+    keep = chain()
+    torch.cuda.synchronize()
+    ref = [o.clone() for o in outs]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        keep = chain()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        keep = chain()
+    for _ in range(2):
+        for o in outs:
+            o.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(outs, ref):
+            assert torch.equal(a, b)
+    del keep

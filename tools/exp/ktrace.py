@@ -20,16 +20,17 @@ psfs = ops.rasterize_psfs(traj, fr, dev, dtype=torch.float16).float()
 ts = ops.compact_taps(psfs, normalize=True)
 plan = bf.prepare_blur([imgs[i] for i in range(B)], ts, list(range(B)), outs=[outs[i, :, :, :1333] for i in range(B)])
 lib = _lib.lib
-lib.dib_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
-lib.dib_debug_trace.restype = ctypes.c_int
+fn = lib.dib_debug_trace_masked if ts.meta[0].prog_group_w == 0 else lib.dib_debug_trace
+fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+fn.restype = ctypes.c_int
 buf = (ctypes.c_uint64 * 65536)()
 for _ in range(3):
     plan.run()
 torch.cuda.synchronize()
-lib.dib_debug_trace(buf, 65536)          # reset
+fn(buf, 65536)          # reset
 plan.run()
 torch.cuda.synchronize()
-n = lib.dib_debug_trace(buf, 65536)
+n = fn(buf, 65536)
 ev = np.frombuffer(buf, dtype=np.uint64)[:n]
 rec = [(int(e >> 24), int((e >> 6) & 0x3f), int(e & 0x3f), int((e >> 12) & 0xfff)) for e in ev]
 rec.sort()
