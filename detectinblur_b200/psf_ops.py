@@ -145,8 +145,11 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
         t = t.contiguous()
         n, iters = int(t.shape[0]), int(t.shape[1])
         t_traj = torch.view_as_real(t).reshape(-1)
-        fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
-        t_fr = torch.as_tensor(fr, device=device)
+        if isinstance(fractions, torch.Tensor) and fractions.is_cuda:
+            t_fr = fractions.to(torch.float64).reshape(-1).expand(n).contiguous()      # already on the device: no staging
+        else:
+            fr = np.array(np.broadcast_to(np.asarray(fractions, dtype=np.float64), (n,)))
+            t_fr = torch.from_numpy(fr).pin_memory().to(device, non_blocking=True)
     else:
         traj = np.ascontiguousarray(np.asarray(trajectories, dtype=np.complex128))
         if traj.ndim == 1:

@@ -242,7 +242,7 @@ def test_device_planned_launch_matches_host_planned(dib):
         assert torch.equal(a, b)
     # the whole chain under a CUDA graph: rasterise (device trajectories) -> compact -> blur, replayed twice
     traj = ops.generate_trajectories(2, [0.005, 0.00005], 3, "cuda")
-    fr = [1 / 5, 1.0]
+    fr = torch.tensor([1 / 5, 1.0], dtype=torch.float64, device="cuda")
     outs = [torch.zeros_like(imgs[0]), torch.zeros_like(imgs[1])]
 
     def chain():

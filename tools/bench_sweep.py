@@ -82,6 +82,40 @@ def main():
                          "device_us": round(dev_us, 1), "wall_us": round(wall_us, 1), "rasterize_us": round(r_us, 1),
                          "compact_us": round(c_us, 1), "blur_us": round(b_us, 1)})
 
+    # ---- batch 1 without a host synchronisation: device-resident trajectories, compact_taps(sync=False) (the launch is
+    #      planned on the device), results into preallocated buffers; issued directly and replayed from a CUDA graph
+    d_traj = [torch.from_numpy(np.ascontiguousarray(traj[k:k + 1])).to(dev) for k in range(n)]
+    d_frac = [torch.tensor([frac[k]], dtype=torch.float64, device=dev) for k in range(n)]
+    d_outs = [torch.empty((3, images[k].shape[1], (images[k].shape[2] + 3) // 4 * 4), device=dev)[:, :, :images[k].shape[2]] for k in range(n)]
+
+    def one_async(k):
+        psf = ops.rasterize_psfs(d_traj[k], d_frac[k], dev, canvas=256, center=True, out_side=128, dtype=torch.float32)
+        ts = ops.compact_taps(psf, normalize=True, max_taps=4096, sync=False)
+        bf.blur_batch([images[k]], ts, [0], outs=[d_outs[k]])
+        return ts
+
+    async_cells = []
+    for k in range(n):
+        a_dev, a_wall = timed(lambda: one_async(k), args.repeats)
+        g_dev = g_wall = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                keep = one_async(k)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                keep = one_async(k)
+            g_dev, g_wall = timed(graph.replay, args.repeats)
+            del keep
+        except Exception as exc:
+            sys.stderr.write("graph capture failed for cell %d: %s\n" % (k, str(exc).splitlines()[0]))
+        async_cells.append({"direct_device_us": round(a_dev, 1), "direct_wall_us": round(a_wall, 1),
+                            "graph_device_us": None if g_dev is None else round(g_dev, 1),
+                            "graph_wall_us": None if g_wall is None else round(g_wall, 1)})
+
     def batched():
         psf = ops.rasterize_psfs(traj, frac, dev, canvas=256, center=True, out_side=128, dtype=torch.float32)
         ts = ops.compact_taps(psf, normalize=True)
@@ -140,6 +174,14 @@ def main():
         "workload": "cfg4: on-the-fly eval sweep, 3 params x 5 exposures, COCO-like sizes, fp32, rasterise + compact + blur",
         "batch1": {"images_per_s_device": n / (b1_dev * 1e-6), "images_per_s_wall": n / (b1_wall * 1e-6),
                    "launches_per_image": 3, "cells": per_cell},
+        "batch1_no_host_sync": {
+            "what": "rasterise (device trajectory) -> compact_taps(sync=False) -> device-planned blur: 5 launches, no read-back",
+            "images_per_s_wall_direct": n / (sum(c["direct_wall_us"] for c in async_cells) * 1e-6),
+            "images_per_s_wall_cuda_graph": (n / (sum(c["graph_wall_us"] for c in async_cells) * 1e-6)
+                                             if all(c["graph_wall_us"] for c in async_cells) else None),
+            "images_per_s_device_cuda_graph": (n / (sum(c["graph_device_us"] for c in async_cells) * 1e-6)
+                                               if all(c["graph_device_us"] for c in async_cells) else None),
+            "cells": async_cells},
         "batched15": {"device_us": bdev, "wall_us": bwall, "images_per_s_device": n / (bdev * 1e-6),
                       "images_per_s_wall": n / (bwall * 1e-6)},
         "rasterizer_batch256": {"device_us": rdev, "wall_us_incl_h2d": rwall, "psfs_per_s_device": 256 / (rdev * 1e-6),
