@@ -312,7 +312,8 @@ def time_steps(step, K, warmup, min_ms=50.0, max_regions=400):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
+        # thread-local capture: other threads of the process (NCCL's watchdog, the clock sampler) keep making CUDA calls
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
             for k in range(K):
                 step(k)
         graph = g
