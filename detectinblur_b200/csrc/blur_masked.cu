@@ -936,7 +936,7 @@ __device__ __forceinline__ void store_rows(const TiledParams& p, const TiledImag
 // ---------------------------------------------------------------- kernel
 // kEpi selects the epilogue variant (kEpiNone / kEpiAffine / kEpiGeneral); batches without one run the leanest.
 template <int kEpi, bool kHalf>
-__global__ void __launch_bounds__(kThreads, 1) blur_tiled_kernel(const __grid_constant__ TiledParams p) {
+__global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_constant__ TiledParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* obuf_all = reinterpret_cast<float*>(smem + 2 * kStageBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes + kOutBufBytes);
@@ -1070,11 +1070,11 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
     DIB_CUDA(cudaGetDevice(&dev));
     if (attr_set_dev != dev) {
         DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiGeneral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiNone, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        DIB_CUDA(cudaFuncSetAttribute(blur_tiled_kernel<kEpiAffine, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_masked_kernel<kEpiNone, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_masked_kernel<kEpiAffine, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_masked_kernel<kEpiGeneral, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_masked_kernel<kEpiNone, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        DIB_CUDA(cudaFuncSetAttribute(blur_masked_kernel<kEpiAffine, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         attr_set_dev = dev;
     }
     TiledParams p;
@@ -1162,15 +1162,15 @@ int launch_tiled(const dib_image* images, const int* order, int n_sel, const dib
             return DIB_ERR_UNSUPPORTED;
         }
         if (any_epi)
-            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, true>, p));
+            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_masked_kernel<kEpiAffine, true>, p));
         else
-            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, true>, p));
+            DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_masked_kernel<kEpiNone, true>, p));
     } else if (any_general) {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiGeneral, false>, p));
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_masked_kernel<kEpiGeneral, false>, p));
     } else if (any_epi) {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiAffine, false>, p));
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_masked_kernel<kEpiAffine, false>, p));
     } else {
-        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_tiled_kernel<kEpiNone, false>, p));
+        DIB_CUDA(cudaLaunchKernelEx(&cfg, blur_masked_kernel<kEpiNone, false>, p));
     }
     DIB_CUDA(cudaGetLastError());
     return DIB_OK;

@@ -446,7 +446,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             (&sh_last[0][0])[k] = -1;
         }
         __syncthreads();
-        for (int i = tid; i < cells; i += kCompactThreads) {
+        const int box_lo = ymin * side, box_hi = (ymax + 1) * side;       // the support's rows only
+        for (int i = box_lo + tid; i < box_hi; i += kCompactThreads) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
             const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
             if (w != 0.0f) {
@@ -460,7 +461,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             }
         }
         __syncthreads();
-        for (int i = tid; i < cells; i += kCompactThreads) {
+        for (int i = box_lo + tid; i < box_hi; i += kCompactThreads) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
             const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
             if (w != 0.0f) {
