@@ -204,11 +204,10 @@ def _half_tiled_ok(images, tapset, psf_indices, outs, noise, noise_sd, clamp, ph
             return False                                   # pass-through images go through the generic kernel's epilogue
         if img.shape[1] <= 64 or img.shape[2] <= 64 or tapset is None or tapset.side > 129:
             return False
-        if tapset.meta is None:
-            return False                                   # device-planned launches: float32 only
-        m = tapset.meta[int(psf_indices[k])]
-        if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM) or m.prog_group_w != 0:
-            return False                                   # in-kernel half I/O is the masked kernel's (small PSFs)
+        if tapset.meta is not None:       # (device-planned tap sets: the kernel is chosen on the device -- small PSFs take the
+            m = tapset.meta[int(psf_indices[k])]           # in-kernel half path, the others the exact-order half loop)
+            if m.count <= 0 or m.prog_chunks <= 0 or (m.flags & _lib.META_NO_PROGRAM) or m.prog_group_w != 0:
+                return False                               # in-kernel half I/O is the masked kernel's (small PSFs)
         if outs is not None and outs[k] is not None:
             o = outs[k]
             if o.dtype != torch.float16 or o.dim() != 3 or o.data_ptr() % 16 or o.stride(1) % 8 or (o.shape[0] > 1 and o.stride(0) % 8):
@@ -296,11 +295,13 @@ def manual_blur(image_GPU, psf_GPU, add_noise=False, noise_level=0.001, add_bloc
 
 
 def blur_image_list(images_GPU, blur_dicts, psfs_GPU, add_noise=False, noise_level=0.001, add_block=False,
-                    add_jpeg_artifact=False, jpeg_compressor=None, exact=None):
+                    add_jpeg_artifact=False, jpeg_compressor=None, exact=None, sync=True):
     """blur_functions.py:92-100: blur, in place, every list entry whose ``blur_dict["blurring"]`` is truthy.
 
     Each PSF is normalised by its own sum (:98) during tap compaction; entries that are not blurred keep their
     identity.  Random draws happen image by image in list order, as in the reference.
+    ``sync=False``: the PSF summaries are not read back and the launch is planned on the device, so the
+    call returns without waiting for the uploads that feed it (``psf_ops.compact_taps(sync=False)``).
     """
     idx = [k for k, bd in enumerate(blur_dicts) if bd["blurring"]]
     if not idx:
@@ -326,7 +327,7 @@ def blur_image_list(images_GPU, blur_dicts, psfs_GPU, add_noise=False, noise_lev
             # the compaction kernel's own normalisation: the sum accumulated in fp64 and rounded once, which equals torch's
             # result for every PSF on the fp16 grid summing to at most 1 (all stored / generated PSFs); a general fp32 PSF
             # may differ from torch's reduction tree by one ulp of the sum
-            tapset = psf_ops.compact_taps(psfs, normalize=True)
+            tapset = psf_ops.compact_taps(psfs, normalize=True, **({} if sync else {"sync": False, "max_taps": 4096}))
         elif psf_dtype == img_dtype:
             # exact=True promises the reference's bits for ANY fp32 PSF: normalise with torch itself, PSF by PSF (:98)
             tapset = psf_ops.compact_taps(torch.stack([p / p.sum() for p in psfs]), normalize=False)

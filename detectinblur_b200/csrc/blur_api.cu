@@ -26,9 +26,15 @@ enum { kPlanned = 3 };      // device-planned: a tiled kernel takes the image if
 // which tiled kernel, if any, takes this image
 static int tiled_kind(const dib_image& im, const dib_psf_meta* meta_host, int io_dtype, bool device_plan) {
     if (device_plan) {
-        // the image-side conditions only; float32 only (the in-kernel half path needs the host to know the kernel)
-        if (im.psf_index < 0 || io_dtype != DIB_F32) return kNotTiled;
+        // the image-side conditions only; which kernel takes the image is decided on the device from its PSF's summary
+        if (im.psf_index < 0) return kNotTiled;
         if ((im.pad_mode != DIB_PAD_REFLECT128 && im.pad_mode != DIB_PAD_ZERO128) || im.H <= 64 || im.W <= 64) return kNotTiled;
+        if (io_dtype == DIB_F16) {
+            // half images: the masked kernel if the PSF is small, else the exact-order kernel (the dense kernel is float32 only)
+            if ((reinterpret_cast<uintptr_t>(im.dst) & 15u) || (im.dst_row_pitch & 7) || (im.dst_chan_pitch & 7)) return kNotTiled;
+            if ((reinterpret_cast<uintptr_t>(im.src) & 1u) || (im.epilogue & ~DIB_EPI_NORMALIZE)) return kNotTiled;
+            return kPlanned;
+        }
         if ((reinterpret_cast<uintptr_t>(im.src) | reinterpret_cast<uintptr_t>(im.dst)) & 3u) return kNotTiled;
         return kPlanned;
     }
@@ -107,7 +113,7 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
             const int kind = tiled_kind(images[k], meta_host, io_dtype, device_plan);
             if (kind == kPlanned) {             // listed for both tiled kernels; each takes its own on the device
                 order[0][n_kind[0]++] = k;
-                order[1][n_kind[1]++] = k;
+                if (io_dtype == DIB_F32) order[1][n_kind[1]++] = k;
                 planned_mask |= 1u << k;
             } else if (kind != kNotTiled) {
                 order[kind - 1][n_kind[kind - 1]++] = k;

@@ -50,7 +50,10 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
     const int n = blockIdx.y;
     if ((p.skip_mask >> n) & 1u) return;
     const dib_image& im = p.img[n];
-    if (((p.planned_mask >> n) & 1u) && im.psf_index >= 0 && psf_program_kind(p.meta[im.psf_index]) != 0) return;
+    if (((p.planned_mask >> n) & 1u) && im.psf_index >= 0) {
+        const int kind = psf_program_kind(p.meta[im.psf_index]);
+        if (sizeof(T) == 2 ? kind == 1 : kind != 0) return;      // half images: only the masked kernel has a half path
+    }
     const int64_t pix = (int64_t)blockIdx.x * kGenericThreads + threadIdx.x;
     if (pix >= (int64_t)im.H * im.W) return;
     const int i = (int)(pix / im.W), j = (int)(pix - (int64_t)i * im.W);

@@ -129,8 +129,9 @@ typedef struct dib_image {
 /* DIB_ALGO_DEVICE_PLAN: plan the launch on the device.  No host copy of the per-PSF summaries is needed (meta_host may be
  * NULL), so nothing has to be read back between dib_compact_taps and dib_blur_batch and the whole chain rasterise -> compact
  * -> blur can be enqueued without a host synchronisation (and captured in a CUDA graph): both tiled kernels and the exact-
- * order kernel are launched and each takes, from the summaries in the tap set, the images that are its own.  float32
- * images; max_taps must hold every PSF of the tap set (a truncated PSF falls to the exact-order kernel with its first
+ * order kernel are launched and each takes, from the summaries in the tap set, the images that are its own (half images:
+ * the masked kernel for small PSFs, the exact-order kernel -- the reference's half loop -- for the others).  max_taps must
+ * hold every PSF of the tap set (a truncated PSF falls to the exact-order kernel with its first
  * max_taps taps -- size the list for the worst case, 4096 covers every 128 x 128 motion PSF). */
 #define DIB_ALGO_DEVICE_PLAN 0x200
 #define DIB_ALGO_SLOT(k) (((k) & 3) << 12)

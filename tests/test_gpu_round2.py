@@ -271,3 +271,20 @@ def test_device_planned_launch_matches_host_planned(dib):
         for a, b in zip(outs, ref):
             assert torch.equal(a, b)
     del keep
+
+
+def test_device_planned_half_images(dib):
+    """Device-planned launches with fp16 images: small PSFs take the masked kernel's in-kernel half path (fp32 accumulation,
+    one rounding: the same bits as the host-planned call), large PSFs the exact-order kernel (the reference's half loop)."""
+    bf, ops = dib
+    np.random.seed(12)
+    small16, _ = po.stored_psf(0.005, 1 / 10, np.random)
+    big16, _ = po.stored_psf(0.00005, 1.0, np.random)
+    psfs = _cuda(np.stack([po.crop128(small16), po.crop128(big16)]))                  # float16 PSFs, as the engines upload them
+    g = torch.Generator().manual_seed(5)
+    imgs = [torch.rand((3, 150, 333), generator=g).cuda().half(), torch.rand((3, 120, 200), generator=g).cuda().half()]
+    ts_host = ops.compact_taps(psfs, normalize=True, max_taps=4096)
+    ts_dev = ops.compact_taps(psfs, normalize=True, max_taps=4096, sync=False)
+    got = bf.blur_batch(imgs, ts_dev, [0, 1])
+    assert torch.equal(got[0], bf.blur_batch(imgs[:1], ts_host, [0])[0])                # masked kernel, in-kernel half I/O
+    assert torch.equal(got[1], bf.blur_batch(imgs[1:], ts_host, [1], exact=True)[0])     # exact-order half loop
