@@ -133,7 +133,7 @@ constexpr int kBandMaxChunks = 8;                                   // 128 rows 
 // a 4-wide weight vector per row, zero where the PSF has no tap (the kernel skips those).  Block-wide; returns through
 // shared memory: chunks (<= 0: none built), weight vectors, segments.
 template <typename T, bool kStaged>
-__device__ void build_program(const T* psf, const float* sh_psf, int side, int normalize, float s, int centre, int ymin, int ymax,
+__device__ void build_program(const T* psf, const float* sh_psf, int side, int normalize, float s, bool s_finite, int centre, int ymin, int ymax,
                               int xmin, int xmax, uint8_t* my_prog, int& out_chunks_n, int& out_steps, int& out_segs) {
     __shared__ unsigned sh_occ[32 * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
@@ -162,7 +162,7 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
             const int x = xmin + g * kGroupW + e;
             if (x < side) {
                 const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                const float w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
                 any |= (w != 0.0f);
             }
         }
@@ -277,7 +277,7 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
                     float w = 0.0f;
                     if (x < side) {
                         const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                        w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                        w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
                     }
                     wout[(sg.woff + step) * kGroupW + e] = w;
                 }
@@ -332,6 +332,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     for (int i = tid; i < cells; i += kCompactThreads) part += (double)psf_cell<T, kStaged>(psf, sh_psf, i);
     const double total = block_sum_double(part, sh_d);
     const float s = PsfNum<T>::round_sum(total);
+    const bool s_finite = s != 0.0f && fabsf(s) <= 3.0e38f;     // false for 0, inf and NaN sums: then every cell is divided, as torch does
 
     // 2. ordered compaction of the normalised PSF (row-major nonzero order, blur_functions.py:63).  Every warp owns a
     //    contiguous slab of the PSF: pass 1 counts its taps (ballot + popc, no block barrier), one scan over the 8 warp
@@ -346,7 +347,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         float v = 0.0f, w = 0.0f;
         if (i < slab_hi) {
             v = psf_cell<T, kStaged>(psf, sh_psf, i);
-            w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
         }
         const bool nz = (w != 0.0f);
         warp_count += __popc(__ballot_sync(0xffffffffu, nz));
@@ -380,7 +381,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         float w = 0.0f;
         if (i < slab_hi) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
-            w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
         }
         const bool nz = (w != 0.0f);
         const unsigned ballot = __ballot_sync(0xffffffffu, nz);
@@ -431,7 +432,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY) && ymax - ymin <= mk::kChunkHaloRows &&
                            xmax - xmin < mk::kChunkGroups * mk::kGroupW;
     int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
-    if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
+    if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, s_finite, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
     if (want_prog && !(small_psf && mk_chunks == 1)) {
         const int nrows_box = ymax - ymin + 1;
         // 3a. rank the candidates (group width 2 / 4) x (shear -kShearMax .. kShearMax) by a cost model: per sheared group
@@ -449,7 +450,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         const int box_lo = ymin * side, box_hi = (ymax + 1) * side;       // the support's rows only
         for (int i = box_lo + tid; i < box_hi; i += kCompactThreads) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
-            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            const float w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
             if (w != 0.0f) {
                 const int y = i / side, x = i - y * side;
 #pragma unroll
@@ -463,7 +464,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         __syncthreads();
         for (int i = box_lo + tid; i < box_hi; i += kCompactThreads) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
-            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+            const float w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
             if (w != 0.0f) {
                 const int y = i / side, x = i - y * side;
 #pragma unroll
@@ -531,7 +532,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                         const int x = xp0 + g * G + shear * (y - ymin) + e;
                         if (x >= 0 && x < side) {
                             const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                            const float w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                            const float w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
                             any |= (w != 0.0f);
                         }
                     }
@@ -667,7 +668,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                             float w = 0.0f;
                             if (x >= 0 && x < side) {
                                 const float v = psf_cell<T, kStaged>(psf, sh_psf, (int64_t)y * side + x);
-                                w = normalize ? PsfNum<T>::normalized(v, s) : v;
+                                w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
                             }
                             wout[(sg.woff + step) * G + e] = w;
                         }
