@@ -149,9 +149,10 @@ extern "C" int dib_blur_batch(const dib_image* images, int n_images, void* tapse
         ++nl;
     }
     if (n_kind[1] > 0) {
-        // its own scheduler words: the two tiled launches of one call may be co-resident
+        // its own scheduler words: the two tiled launches of one call may be co-resident -- and are meant to be: they work on
+        // different images of the batch, so the second one never waits for the first (it starts on the SMs that one vacates)
         const int rc = launch_tiled(images, order[1], n_kind[1], meta_host, prog, sched + kSchedSlots, philox_seed, philox_offset, io_dtype,
-                                    overlap_prev, plan_meta, st);
+                                    overlap_prev || n_kind[0] > 0, plan_meta, st);
         if (rc != DIB_OK) return rc;
         ++nl;
     }

@@ -76,6 +76,7 @@ __device__ inline int block_min_int(int v, int* sh) {
 
 constexpr int kMaxGroups = 192;       // sheared groups of one PSF (support width + shear drift, in groups of 2)
 constexpr int kMaxBands = 64;
+constexpr int kMaskedMaxChunks = 4;      // PSFs whose masked program needs more chunks take the dense sheared kernel
 constexpr int kNumShears = 2 * kShearMax + 1;
 constexpr int kNumCand = 2 * kNumShears;          // group width 2 or 4 x shear -kShearMax .. kShearMax
 
@@ -427,13 +428,15 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     }
     int prog_G = 0, prog_k = 0;
     __syncthreads();
-    // A PSF whose support fits one chunk of the masked kernel's program (every low-exposure PSF) takes that kernel: it is
-    // the faster one there; everything else gets the dense sheared program.
-    const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY) && ymax - ymin <= mk::kChunkHaloRows &&
-                           xmax - xmin < mk::kChunkGroups * mk::kGroupW;
+    // Which tiled kernel takes the PSF is decided here, by measurement (tools/exp/route_probe.py, 8 x 3x800x1333 per cell of
+    // the eval sweep): the masked kernel is the faster one for every PSF its program holds in up to kMaskedMaxChunks chunks
+    // (all exposures up to 1/2, full exposure at param 0.005 / 0.001); the long streaks of param 0.00005 at full exposure,
+    // which it cuts into 5-6 chunks, run 5 % faster on the dense sheared kernel.
+    const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY);
     int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
     if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, s_finite, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
-    if (want_prog && !(small_psf && mk_chunks == 1)) {
+    const bool masked_ok = small_psf && mk_chunks > 0 && (mk_chunks <= kMaskedMaxChunks || (flags_in & DIB_COMPACT_MASKED_ONLY));
+    if (want_prog && !masked_ok) {
         const int nrows_box = ymax - ymin + 1;
         // 3a. rank the candidates (group width 2 / 4) x (shear -kShearMax .. kShearMax) by a cost model: per sheared group
         //     the span of rows it occupies -> dense steps, window fills and chunks.
@@ -682,8 +685,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         }
     }
     int nchunks_final = want_prog ? sh_nchunks : -1;
-    if (small_psf && mk_chunks == 1) {           // masked program: group width 0 in the summary
-        nchunks_final = 1;
+    if (masked_ok) {           // masked program: group width 0 in the summary
+        nchunks_final = mk_chunks;
         prog_G = 0;
         prog_k = 0;
         if (tid == 0) {
@@ -731,7 +734,7 @@ extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int
     DIB_CHECK_ARG(psf_stride >= (int64_t)side * side, "dib_compact_taps: psf_stride %lld smaller than one PSF",
                   (long long)psf_stride);
     DIB_CHECK_ARG(max_taps > 0, "dib_compact_taps: max_taps must be > 0");
-    DIB_CHECK_ARG((normalize & ~(DIB_COMPACT_NORMALIZE | DIB_COMPACT_DENSE_ONLY)) == 0, "dib_compact_taps: unknown flag bits 0x%x", normalize);
+    DIB_CHECK_ARG((normalize & ~(DIB_COMPACT_NORMALIZE | DIB_COMPACT_DENSE_ONLY | DIB_COMPACT_MASKED_ONLY)) == 0, "dib_compact_taps: unknown flag bits 0x%x", normalize);
     DIB_CHECK_ARG(psf_dtype == DIB_F32 || psf_dtype == DIB_F16, "dib_compact_taps: PSF dtype must be DIB_F32 or DIB_F16");
     const dib_tapset_layout L = tapset_layout(n_psfs, max_taps);
     uint8_t* base = static_cast<uint8_t*>(tapset);

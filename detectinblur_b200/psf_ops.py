@@ -114,7 +114,7 @@ def compact_taps(psfs, normalize, max_taps=1024, dense_only=None, sync=True):
     buf = torch.empty(lay.total_bytes, dtype=torch.uint8, device=psfs.device)
     with torch.cuda.device(psfs.device):
         _lib.check(_lib.lib.dib_compact_taps(ctypes.c_void_p(psfs.data_ptr()), _TORCH_TO_DIB[psfs.dtype], n, side,
-                                             side * side, (1 if normalize else 0) | (2 if dense_only else 0), ctypes.c_void_p(buf.data_ptr()),
+                                             side * side, (1 if normalize else 0) | (2 if dense_only else 0) | (4 if os.environ.get("DIB_MASKED_ONLY", "0") not in ("0", "") else 0), ctypes.c_void_p(buf.data_ptr()),
                                              int(max_taps), _stream_ptr(psfs.device)))
         if not sync:
             return TapSet(buf, lay, n, int(max_taps), side, None)

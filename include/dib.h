@@ -156,6 +156,7 @@ DIB_API int dib_device_info(int* sm_count, int* cc);
  */
 #define DIB_COMPACT_NORMALIZE 1
 #define DIB_COMPACT_DENSE_ONLY 2
+#define DIB_COMPACT_MASKED_ONLY 4   /* measurements: the masked kernel's program for every PSF it can hold (several chunks) */
 DIB_API int dib_tapset_layout_for(int n_psfs, int max_taps, dib_tapset_layout* out);
 DIB_API int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int side, int64_t psf_stride, int normalize,
                      void* tapset, int max_taps, void* stream);
