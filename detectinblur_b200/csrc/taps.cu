@@ -432,7 +432,12 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     // the eval sweep): the masked kernel is the faster one for every PSF its program holds in up to kMaskedMaxChunks chunks
     // (all exposures up to 1/2, full exposure at param 0.005 / 0.001); the long streaks of param 0.00005 at full exposure,
     // which it cuts into 5-6 chunks, run 5 % faster on the dense sheared kernel.
-    const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY);
+    // A masked chunk spans at most kChunkHaloRows + 1 tap rows and kChunkGroups * kGroupW tap columns: a support box that
+    // cannot fit kMaskedMaxChunks of them goes to the dense builder directly (saves the masked build, ~40 us for one PSF).
+    const int mk_bound = max((ymax - ymin + mk::kChunkHaloRows + 1) / (mk::kChunkHaloRows + 1),
+                             (xmax - xmin + mk::kChunkGroups * mk::kGroupW) / (mk::kChunkGroups * mk::kGroupW));
+    const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY) &&
+                           (mk_bound <= kMaskedMaxChunks || (flags_in & DIB_COMPACT_MASKED_ONLY));
     int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
     if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, s_finite, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
     const bool masked_ok = small_psf && mk_chunks > 0 && (mk_chunks <= kMaskedMaxChunks || (flags_in & DIB_COMPACT_MASKED_ONLY));
