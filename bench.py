@@ -398,7 +398,7 @@ def e2e_variant(kind, wl, dev, world, steps):
     import detectinblur_b200.blur_functions as bf
     import detectinblur_b200.psf_ops as ops
     B = wl.B
-    n_streams = 3
+    n_streams = int(os.environ.get("DIB_E2E_STREAMS", "3"))
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     if kind == "u8":
         hin = [(hb.float() * 255).to(torch.uint8).pin_memory() for hb in wl.host_batches]
@@ -417,9 +417,12 @@ def e2e_variant(kind, wl, dev, world, steps):
     hpsf = wl.host_psfs.to(comp).pin_memory()
     in_bytes += hpsf.numel() * hpsf.element_size()
 
+    host_s = []
+
     def step(k):
         st = streams[k % n_streams]
         st.synchronize()                      # the step that used this stream's buffers three steps ago is complete
+        t_enq = time.perf_counter()
         with torch.cuda.stream(st):
             dbatch = hin[k % wl.n_rot].to(dev, non_blocking=True)
             dpsf = hpsf.to(dev, non_blocking=True)
@@ -447,10 +450,12 @@ def e2e_variant(kind, wl, dev, world, steps):
                     r = images[i]
                     full = r.as_strided((C, H, r.stride(1)), (r.stride(0), r.stride(1), 1))
                     hout[k % n_streams][i, :, :, :r.stride(1)].copy_(full, non_blocking=True)
+        host_s.append(time.perf_counter() - t_enq)
 
     for k in range(6):
         step(k)
     torch.cuda.synchronize()
+    del host_s[:]
     regions = []
     for _ in range(3):
         if world > 1:
@@ -468,7 +473,7 @@ def e2e_variant(kind, wl, dev, world, steps):
         regions.append(t)
     med = float(np.median(regions))
     return {"value": world * B * steps / med, "unit": "images/s", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
-            "steps": steps, "regions_s": regions, "io": kind,
+            "steps": steps, "regions_s": regions, "io": kind, "host_enqueue_us_per_step": round(float(np.median(host_s)) * 1e6, 1),
             "api": "blur_image_list(images, blur_dicts, psfs%s) on pinned host buffers, %d streams%s" % (
                 ", sync=False", n_streams, "; psf_ops.u8_to_float / float_to_u8 around it" if kind == "u8" else "")}
 

@@ -1048,7 +1048,11 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[b]);     // this warp is done reading the stage
             DIB_TRACE_EVENT(4, n);
+#ifdef DIB_NOSTORE      // experiment: upper bound of what hiding the store phase could gain (results are not written)
+            if (h.last_chunk && active && acc[0][0].x == 12345.678f) store_rows<kEpi, kHalf>(p, im, h.ch, row0, col0, acc, obuf);
+#else
             if (h.last_chunk && active) store_rows<kEpi, kHalf>(p, im, h.ch, row0, col0, acc, obuf);
+#endif
             DIB_TRACE_EVENT(5, n);
         }
     }
