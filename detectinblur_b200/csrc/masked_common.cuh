@@ -1,6 +1,7 @@
-// Program format of the MASKED tiled kernel (blur_masked.cu): the round-1 kernel, kept for PSFs whose whole support fits
-// one chunk (<= 18 rows x 20 columns: every low-exposure PSF), where it is the faster of the two tiled kernels.  Larger
-// PSFs get the dense sheared program of dib_common.cuh (blur_tiled.cu).  Names live in dib::mk and shadow the dense
+// Program format of the MASKED tiled kernel (blur_masked.cu): the round-1 kernel, kept for PSFs whose program fits
+// kMaskedMaxChunks (taps.cu: 4) chunks of <= 18 rows x 20 columns -- every low-exposure PSF and most high-exposure ones --
+// where it is the faster of the two tiled kernels (tools/exp/route_probe.py).  Larger PSFs get the dense sheared program
+// of dib_common.cuh (blur_tiled.cu).  Names live in dib::mk and shadow the dense
 // kernel's geometry constants of the same name.
 #pragma once
 #include "dib_common.cuh"
