@@ -61,8 +61,12 @@ def main():
             u = units[hdr.index(k)].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         per = [val("dram__bytes_read.sum", r) + val("dram__bytes_write.sum", r) for r in data]
-        json.dump({"dram_bytes_per_launch": sum(per) / len(per), "launches": len(per), "source": rep,
-                   "kernel": data[0][name_i][:60]}, open(traffic, "w"))
+        if "--per-step" in sys.argv:      # the captured launches are the kernels of ONE step (e.g. masked + dense): sum them
+            json.dump({"dram_bytes_per_launch": sum(per), "launches": len(per), "source": rep, "per_kernel": per,
+                       "kernel": " + ".join(r[name_i][:40] for r in data)}, open(traffic, "w"))
+        else:
+            json.dump({"dram_bytes_per_launch": sum(per) / len(per), "launches": len(per), "source": rep,
+                       "kernel": data[0][name_i][:60]}, open(traffic, "w"))
     print("wrote", out + ".csv", out + ".md", traffic or "")
 
 
