@@ -56,11 +56,18 @@ constexpr int kComputeWarps = kWarpRows * kWarpCols;       // a multiple of 4: e
 constexpr int kProducerWarps = 4;           // one more warpgroup: every thread stages at most one tile row
 constexpr int kThreads = (kComputeWarps + kProducerWarps) * 32;
 constexpr int kProducerRegs = 56;   // setmaxnreg budgets; together they must fit the 64K-register file
+#ifndef DIB_MK_HALF_PRODUCER_REGS
+#define DIB_MK_HALF_PRODUCER_REGS 96
+#endif
+// the half-precision producers also widen the rows and hold a row's unaligned ends in registers while the copies land: at
+// 56 registers that spilled, and the spill stores made the issue phase wait for the global loads
+constexpr int kProducerRegsHalf = DIB_MK_HALF_PRODUCER_REGS;
 // setmaxnreg moves registers inside the CTA's launch-time allocation (threads x the per-thread count the launch bound
 // allows, a multiple of 8); asking for more than the producers hand back blocks forever.
 constexpr int kLaunchRegs = (65536 / kThreads) / 8 * 8 > 255 ? 248 : (65536 / kThreads) / 8 * 8;
 constexpr int kComputeRegsRaw = (kThreads * kLaunchRegs - kProducerWarps * 32 * kProducerRegs) / (kComputeWarps * 32) / 8 * 8;
 constexpr int kComputeRegs = kComputeRegsRaw > 232 ? 232 : kComputeRegsRaw;
+constexpr int kComputeRegsHalf = (kThreads * kLaunchRegs - kProducerWarps * 32 * kProducerRegsHalf) / (kComputeWarps * 32) / 8 * 8;
 static_assert(kComputeWarps % 4 == 0, "warpgroup-aligned compute warps");
 constexpr int kTH = kWarpRows * kRows;      // 36 output rows per tile
 constexpr int kTW = kWarpCols * kWarpW;     // 448 output columns per tile
@@ -310,12 +317,14 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
 
 // Hand the producer group its next tile.  Thread 0 of the group takes a ticket from the global counter and shares
 // it through shared memory; the two slots alternate so one named barrier per fetch is enough.
-__device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int& nfetch, int pt) {
+constexpr unsigned kNoTicket = 0xffffffffu;
+__device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int& nfetch, int pt, unsigned pre = kNoTicket) {
     int* slot = slots + (nfetch & 1);
     if (pt == 0) {
         // the first tile of a CTA is its block index (no round trip to the counter before the first load can go out);
-        // tickets from the counter follow after the gridDim.x tiles handed out that way
-        const unsigned t = nfetch == 0 ? blockIdx.x : gridDim.x + atomicAdd(&p.sched->next_tile, 1u);
+        // tickets from the counter follow after the gridDim.x tiles handed out that way.  `pre`: a ticket thread 0 drew
+        // earlier (the atomic's round trip then overlaps the work in between)
+        const unsigned t = nfetch == 0 ? blockIdx.x : gridDim.x + (pre != kNoTicket ? pre : atomicAdd(&p.sched->next_tile, 1u));
         *slot = t < (unsigned)p.total_tiles ? (int)t : -1;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
@@ -324,7 +333,8 @@ __device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int&
 }
 
 // successor of a stage: next chunk of the same tile, else chunk 0 of the next tile the scheduler hands out
-__device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cur, Stage& nx, int* slots, int& nfetch, int pt) {
+__device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cur, Stage& nx, int* slots, int& nfetch, int pt,
+                                           unsigned pre = kNoTicket) {
     if (cur.tile < 0) {
         nx.tile = -1;
         return;
@@ -334,7 +344,8 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
         nx.chunk = cur.chunk + 1;
     } else {
         do {        // device-planned launches: tiles of images that belong to another kernel are skipped
-            nx.tile = fetch_tile(p, slots, nfetch, pt);
+            nx.tile = fetch_tile(p, slots, nfetch, pt, pre);
+            pre = kNoTicket;
             if (nx.tile < 0) return;
             nx.chunk = 0;
             decode_tile(p, nx.tile, nx);
@@ -487,7 +498,9 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
         head[j] = (in_rows && !zero_row && xa + j < xa_al) ? gp[xa + j] : __half(0.0f);
         tail[j] = (in_rows && !zero_row && xb_al + j < xb1) ? gp[xb_al + j] : __half(0.0f);
     }
+    DIB_TRACE_EVENT(10, 0);
     producer_wait(landed, landed_parity, pt);
+    DIB_TRACE_EVENT(11, 0);
     float* drow = sm.tile + ro - cl;                  // drow[col] addresses image column col
     // Widen the aligned interiors in place.  A warp takes the rows its own lanes placed, one row at a time, a lane per
     // group of 8 elements: every lane first reads its 16 bytes of halves, then -- after a warp barrier -- writes its 32
@@ -504,24 +517,34 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
         uint32_t hb = tile_b + 2u * kPitch * (uint32_t)(pw + 1) + 8u * (uint32_t)lane;      // row pw's halves; + 2 * off
         const uint32_t fb = tile_b + 16u * (uint32_t)lane;                                    // + 4 * off
         const int nl = (nrows - pw + kProducerWarps - 1) / kProducerWarps;                   // rows this warp placed
-        for (int l = 0; l < nl; ++l, hb += 2u * kPitch * kProducerWarps) {
-            const int pk = __shfl_sync(0xffffffffu, packed, l);
-            const uint32_t off = (uint32_t)(pk & 0xfffff);
-            const int n4 = (pk >> 20) * 2;                                  // 4-element chunks of the row (<= 120)
-            const uint32_t h0 = hb + 2u * off, f0 = fb + 4u * off;
-            uint2 hv[4];
+        // two rows per round: the second row's loads are in flight while the first row's latency passes
+        for (int l = 0; l < nl; l += 2, hb += 4u * kPitch * kProducerWarps) {
+            uint2 hv[2][4];
+            uint32_t f0[2];
+            int n4[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                hv[j] = make_uint2(0u, 0u);
-                if (lane + 32 * j < n4) hv[j] = lds_v2u(h0 + 256u * j);
+            for (int q = 0; q < 2; ++q) {
+                const int pk = __shfl_sync(0xffffffffu, packed, min(l + q, 31));
+                const uint32_t off = (uint32_t)(pk & 0xfffff);
+                n4[q] = (l + q < nl) ? (pk >> 20) * 2 : 0;                   // 4-element chunks of the row (<= 120)
+                const uint32_t h0 = hb + 2u * off + (uint32_t)q * (2u * kPitch * kProducerWarps);
+                f0[q] = fb + 4u * off;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hv[q][j] = make_uint2(0u, 0u);
+                    if (lane + 32 * j < n4[q]) hv[q][j] = lds_v2u(h0 + 256u * j);
+                }
             }
-            __syncwarp();                                                  // the whole row is read before any of it is written
+            __syncwarp();                                                  // both rows are read before any of them is written
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (lane + 32 * j < n4) sts_widened(f0 + 512u * j, hv[j]);
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (lane + 32 * j < n4[q]) sts_widened(f0[q] + 512u * j, hv[q][j]);
         }
         __syncwarp();
     }
+    DIB_TRACE_EVENT(12, 0);
     if (in_rows && zero_row) {
         for (int col = cl; col <= cr; ++col) drow[col] = 0.0f;
     } else if (in_rows) {
@@ -544,14 +567,19 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
             const int irow = rt + r2;
             float v = 0.0f;
             bool write = true;
+            float* rowp = sm.tile + sm.rowtab[r2] - cl;        // rowp[c] is image column c of the staged (mirrored) row
             if (im.zero_pad) {
                 write = irow >= 0 && irow < im.H;            // rows outside the image are already all zeros
             } else {
-                v = __half2float(plane[(int64_t)reflect101(irow, im.H) * im.src_rp + reflect101(col, im.W)]);
+                // a reflect-101 pixel beside the image is another pixel of the same staged row (widened above): no trip to
+                // global memory -- unless the tile holds so few image columns that the mirror lies left of what was staged
+                const int mc = reflect101(col, im.W);
+                v = (mc >= xa && mc < xb1) ? rowp[mc] : __half2float(plane[(int64_t)reflect101(irow, im.H) * im.src_rp + mc]);
             }
-            if (write) sm.tile[sm.rowtab[r2] - cl + col] = v;
+            if (write) rowp[col] = v;
         }
     }
+    DIB_TRACE_EVENT(16, 0);
     mbar_arrive(full);          // release: this thread's shared-memory writes are visible to whoever observes the phase
 }
 
@@ -968,11 +996,15 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
     // Register budget: the launch splits the register file evenly over all warps; the producer warpgroup hands most of
     // its share back so that the compute warps can hold kR * kCC accumulators + kR * kWinW window values per thread.
     if (warp < kProducerWarps) {        // producers are the lowest warp ids: the issue arbiter favours high ids
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if constexpr (kHalf)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegsHalf));
+        else
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         // ------------------------------------------------ producer warpgroup
         const int pt = threadIdx.x;
         Stage cur, nxt;
         int nfetch = 0;
+        unsigned pre_ticket = kNoTicket;
         cur.chunk = 0;
         do {        // (device-planned launches skip the tiles of images that belong to another kernel)
             cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
@@ -982,11 +1014,18 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
         if (cur.tile >= 0) cur.rec = load_chunk_rec(p, cur.img, 0);
         for (int n = 0;; ++n) {
             const int b = n & 1;
-            next_stage(p, cur, nxt, tile_slots, nfetch, pt);          // its chunk record is in flight during the issue below
+            DIB_TRACE_EVENT(15, n);
+            next_stage(p, cur, nxt, tile_slots, nfetch, pt, pre_ticket);     // its chunk record is in flight during the issue below
+            pre_ticket = kNoTicket;
+            // half path: the producers are busy for the whole stage (they widen the rows), so the ticket the NEXT call of
+            // next_stage will need is drawn now and its round trip to the counter hides behind this stage's work
+            if (kHalf && pt == 0 && nxt.tile >= 0 && nxt.chunk + 1 >= nxt.nchunks) pre_ticket = atomicAdd(&p.sched->next_tile, 1u);
+            DIB_TRACE_EVENT(13, n);
             const bool wait_empty = n >= 2;
             const uint32_t empty_parity = (uint32_t)(((n >> 1) - 1) & 1);
             // the float path waits inside issue_stage, after the row arithmetic
             if ((kHalf || cur.tile < 0) && wait_empty) producer_wait(&empty[b], empty_parity, pt);
+            DIB_TRACE_EVENT(14, n);
             const StageSmem sm = stage_smem(smem, b);
             if (cur.tile < 0) {
                 if (pt == 0) sm.hdr->tile = -1;
@@ -1014,7 +1053,10 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
             cur = nxt;
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
+        if constexpr (kHalf)
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegsHalf));
+        else
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kComputeRegs));
         // ------------------------------------------------ compute warps
         const int cw = warp - kProducerWarps;
         const int wrow = cw / kWarpCols, wcol = cw % kWarpCols;

@@ -13,8 +13,9 @@ spec = bench.workload_spec(name, None)
 B = spec["batch"]
 dev = torch.device("cuda", 0)
 gen = torch.Generator(device="cpu").manual_seed(1337)
-imgs = torch.rand((B, 3, 800, 1333), generator=gen).to(dev)
-outs = torch.zeros((B, 3, 800, 1336), device=dev)
+dt = torch.float16 if spec.get("dtype") == "f16" or name.endswith("h") else torch.float32
+imgs = torch.rand((B, 3, 800, 1333), generator=gen).to(dev).to(dt)
+outs = torch.zeros((B, 3, 800, 1336), device=dev, dtype=dt)
 traj, fr = bench.make_trajectories(spec, seed=0)
 psfs = ops.rasterize_psfs(traj, fr, dev, dtype=torch.float16).float()
 ts = ops.compact_taps(psfs, normalize=True)
