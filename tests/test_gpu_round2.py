@@ -288,3 +288,39 @@ def test_device_planned_half_images(dib):
     got = bf.blur_batch(imgs, ts_dev, [0, 1])
     assert torch.equal(got[0], bf.blur_batch(imgs[:1], ts_host, [0])[0])                # masked kernel, in-kernel half I/O
     assert torch.equal(got[1], bf.blur_batch(imgs[1:], ts_host, [1], exact=True)[0])     # exact-order half loop
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+def test_rasterizer_cluster_splits_are_bit_identical(dib, golden_dir, split, monkeypatch):
+    """The rasteriser spreads one PSF over a cluster of 1 / 2 / 4 / 8 CTAs (chosen from the batch size; forced here): cells
+    and output pixels are divided among the CTAs, sum and centroid repeated by each.  Every split must give the golden
+    fp64 PSFs of the reference's PSF.fit() + centerPSF() bit for bit (generate_PSF.py:31-123), offsets included."""
+    bf, ops = dib
+    g = np.load(os.path.join(golden_dir, "psf_cases.npz"))
+    n = int(g["n"])
+    xs = np.stack([g["x_%d" % k] for k in range(n)])
+    fr = np.array([g["meta_%d" % k][1] for k in range(n)])
+    monkeypatch.setenv("DIB_RASTER_SPLIT", str(split))
+    cen, offs = ops.rasterize_psfs(xs, fr, "cuda", canvas=256, center=True, out_side=256, dtype=torch.float64, return_offsets=True)
+    cen = cen.cpu().numpy()
+    for k in range(n):
+        ref_cen = np.zeros(256 * 256)
+        ref_cen[g["cen_idx_%d" % k]] = g["cen_val_%d" % k]
+        assert np.array_equal(cen[k].ravel(), ref_cen), (split, k)
+        ref_raw = np.zeros(256 * 256)
+        ref_raw[g["raw_idx_%d" % k]] = g["raw_val_%d" % k]
+        assert tuple(offs[k].cpu().numpy()) == po.centroid_offsets(ref_raw.reshape(256, 256)), (split, k)
+    # a batch large enough for the default rule to pick every split size: PSF k is the same whatever batch it is part of
+    monkeypatch.delenv("DIB_RASTER_SPLIT")
+    if split != 1:
+        return
+    reps = 170 // n + 1
+    big_x, big_f = np.concatenate([xs] * reps), np.concatenate([fr] * reps)
+    for count in (n, 40, 100, 170):
+        out = ops.rasterize_psfs(big_x[:count], big_f[:count], "cuda", canvas=256, center=True, out_side=128,
+                                 dtype=torch.float16).cpu().numpy()
+        for k in range(count):
+            ref_cen = np.zeros(256 * 256)
+            ref_cen[g["cen_idx_%d" % (k % n)]] = g["cen_val_%d" % (k % n)]
+            assert np.array_equal(out[k], ref_cen.reshape(256, 256).astype(np.float16)[64:192, 64:192]), (count, k)
