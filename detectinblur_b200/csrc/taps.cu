@@ -35,42 +35,27 @@ struct PsfNum<__half> {
     __device__ static float normalized(float v, float s) { return __half2float(__float2half_rn(__fdiv_rn(v, s))); }
 };
 
-__device__ inline double block_sum_double(double v, double* sh) {
+#ifdef DIB_COMPACT_TIMING       // experiment build: phase timestamps of block 0 (tools/exp/time_compact.py)
+__device__ unsigned long long g_compact_t[16];
+#define DIB_CT(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_compact_t[k] = clock64(); } while (0)
+#else
+#define DIB_CT(k)
+#endif
+
+static_assert(kCompactThreads == 1024, "the two-level reductions below assume 32 warps");
+
+// Block-wide fp64 sum: shuffle tree inside each warp, then the same tree over the 32 warp totals (a fixed order, so the
+// result is deterministic), one barrier pair instead of a 32-term serial loop in every thread.
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
     if (lane == 0) sh[warp] = v;
     __syncthreads();
-    double t = 0.0;
+    double t = sh[lane];
 #pragma unroll
-    for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[w];  // fixed order: deterministic
-    return t;
-}
-
-__device__ inline long long block_sum_ll(long long v, long long* sh) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    long long t = 0;
-#pragma unroll
-    for (int w = 0; w < kCompactThreads / 32; ++w) t += sh[w];
-    return t;
-}
-
-__device__ inline int block_min_int(int v, int* sh) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    int t = sh[0];
-#pragma unroll
-    for (int w = 1; w < kCompactThreads / 32; ++w) t = min(t, sh[w]);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     return t;
 }
 
@@ -135,7 +120,7 @@ constexpr int kBandMaxChunks = 8;                                   // 128 rows 
 // shared memory: chunks (<= 0: none built), weight vectors, segments.
 template <typename T, bool kStaged>
 __device__ void build_program(const T* psf, const float* sh_psf, int side, int normalize, float s, bool s_finite, int centre, int ymin, int ymax,
-                              int xmin, int xmax, uint8_t* my_prog, int& out_chunks_n, int& out_steps, int& out_segs) {
+                              int xmin, int xmax, uint8_t* my_prog, int max_chunks, int& out_chunks_n, int& out_steps, int& out_segs) {
     __shared__ unsigned sh_occ[32 * 4];
     __shared__ ChunkRec sh_chunks[kProgMaxChunks];
     __shared__ SegRec sh_segs[kProgMaxChunks * kChunkGroups];
@@ -232,6 +217,12 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
     }
     __syncthreads();
     int nchunks = sh_nchunks;
+    if (nchunks > max_chunks) {     // the caller will not use a program this long: skip the offsets and the weight vectors
+        out_chunks_n = nchunks;
+        out_steps = 0;
+        out_segs = 0;
+        return;
+    }
     // 3c. offsets: weight vectors of a chunk's segments are laid out back to back
     if (nchunks > 0) {
         if (tid == 0) {
@@ -297,8 +288,8 @@ __global__ void __launch_bounds__(kCompactThreads)
 compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, int flags_in, dib_psf_meta* __restrict__ meta,
                     dib_tap* __restrict__ taps, int max_taps, uint8_t* __restrict__ prog, SchedWords* __restrict__ sched) {
     __shared__ double sh_d[kCompactThreads / 32];
-    __shared__ long long sh_ll[kCompactThreads / 32];
-    __shared__ int sh_i[kCompactThreads / 32];
+    __shared__ int sh_min4[4];                       // ymin, -ymax, xmin, -xmax of the taps
+    __shared__ unsigned long long sh_sum6[6];        // support and first / second moments of the positive cells
     __shared__ int sh_warp_count[kCompactThreads / 32];
     __shared__ int sh_running;
     __shared__ unsigned sh_occ[kMaxGroups * 4];
@@ -310,6 +301,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ unsigned long long sh_cost[kNumCand];
     __shared__ int sh_nchunks, sh_nsegs, sh_total_steps, sh_choice;
 
+    DIB_CT(0);
     const int normalize = flags_in & DIB_COMPACT_NORMALIZE;
     const int n = blockIdx.x;
     if (n == 0 && threadIdx.x == 0) {
@@ -321,6 +313,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const T* psf = psfs + (int64_t)n * psf_stride;
     const int cells = side * side;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 4) sh_min4[tid] = 1 << 20;
+    if (tid >= 32 && tid < 38) sh_sum6[tid - 32] = 0ull;        // (published by the barriers of the sum below)
     extern __shared__ float sh_psf[];
     if constexpr (kStaged) {
 #pragma unroll 16
@@ -328,6 +322,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         __syncthreads();
     }
 
+    DIB_CT(1);
     // 1. psf.sum() (blur_functions.py:98)
     double part = 0.0;
     for (int i = tid; i < cells; i += kCompactThreads) part += (double)psf_cell<T, kStaged>(psf, sh_psf, i);
@@ -335,14 +330,19 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const float s = PsfNum<T>::round_sum(total);
     const bool s_finite = s != 0.0f && fabsf(s) <= 3.0e38f;     // false for 0, inf and NaN sums: then every cell is divided, as torch does
 
+    DIB_CT(2);
     // 2. ordered compaction of the normalised PSF (row-major nonzero order, blur_functions.py:63).  Every warp owns a
     //    contiguous slab of the PSF: pass 1 counts its taps (ballot + popc, no block barrier), one scan over the 8 warp
     //    totals gives each slab its output offset, pass 2 writes the taps in order.
     int ymin = 1 << 20, ymax_neg = 1 << 20, xmin = 1 << 20, xmax_neg = 1 << 20;  // max kept as min of negatives
-    long long sy = 0, sx = 0, syy = 0, sxx = 0, sxy = 0, support = 0;
+    // per-thread moment sums stay in 32 bits (a thread sees <= slab / 32 cells of coordinates < 512) and widen at the reduction
+    int support_i = 0, sy_i = 0, sx_i = 0, syy_i = 0, sxx_i = 0, sxy_i = 0;
     const int slab = ((cells + kCompactThreads / 32 - 1) / (kCompactThreads / 32) + 31) & ~31;
     const int slab_lo = warp * slab, slab_hi = min(cells, slab_lo + slab);
+    const int lg_side = (side & (side - 1)) == 0 ? 31 - __clz(side) : -1;       // row of a cell by shift when side is 2^k
+    // (loops kept rolled: the kernel runs every instruction about once, so code size is fetch time)
     int warp_count = 0;
+#pragma unroll 1
     for (int base = slab_lo; base < slab_hi; base += 32) {
         const int i = base + lane;
         float v = 0.0f, w = 0.0f;
@@ -353,7 +353,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         const bool nz = (w != 0.0f);
         warp_count += __popc(__ballot_sync(0xffffffffu, nz));
         if (nz || v > 0.0f) {
-            const int y = i / side, x = i - y * side;
+            const int y = lg_side >= 0 ? i >> lg_side : i / side, x = i - y * side;
             if (nz) {
                 ymin = min(ymin, y);
                 ymax_neg = min(ymax_neg, -y);
@@ -361,56 +361,97 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                 xmax_neg = min(xmax_neg, -x);
             }
             if (v > 0.0f) {  // support of the PCA: psf > 0 (transforms.py:366)
-                support += 1;
-                sy += y;
-                sx += x;
-                syy += (long long)y * y;
-                sxx += (long long)x * x;
-                sxy += (long long)y * x;
+                support_i += 1;
+                sy_i += y;
+                sx_i += x;
+                syy_i += y * y;
+                sxx_i += x * x;
+                sxy_i += y * x;
             }
         }
     }
     if (lane == 0) sh_warp_count[warp] = warp_count;
     __syncthreads();
+    DIB_CT(3);
     int offset = 0, total_count = 0;
-    for (int k = 0; k < kCompactThreads / 32; ++k) {
-        if (k < warp) offset += sh_warp_count[k];
-        total_count += sh_warp_count[k];
+    {
+        const int c = sh_warp_count[lane];          // 32 warps: exclusive prefix over the warp totals by shuffle
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        total_count = __shfl_sync(0xffffffffu, incl, 31);
+        offset = __shfl_sync(0xffffffffu, incl - c, warp);
     }
-    for (int base = slab_lo; base < slab_hi; base += 32) {
-        const int i = base + lane;
-        float w = 0.0f;
-        if (i < slab_hi) {
-            const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
-            w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;   // 0 / s is 0 for a finite nonzero sum
+    if (warp_count != 0) {      // warp-uniform: most slabs of a 128 x 128 container hold no tap at all
+#pragma unroll 1
+        for (int base = slab_lo; base < slab_hi; base += 32) {
+            const int i = base + lane;
+            float w = 0.0f;
+            if (i < slab_hi) {
+                const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
+                w = (normalize && (v != 0.0f || !s_finite)) ? PsfNum<T>::normalized(v, s) : v;
+            }
+            const bool nz = (w != 0.0f);
+            const unsigned ballot = __ballot_sync(0xffffffffu, nz);
+            const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
+            if (nz && pos < max_taps) {
+                const int y = lg_side >= 0 ? i >> lg_side : i / side, x = i - y * side;
+                dib_tap t;
+                t.y = (int16_t)y;
+                t.x = (int16_t)x;
+                t.w = w;
+                taps[(int64_t)n * max_taps + pos] = t;
+            }
+            offset += __popc(ballot);
         }
-        const bool nz = (w != 0.0f);
-        const unsigned ballot = __ballot_sync(0xffffffffu, nz);
-        const int pos = offset + __popc(ballot & ((1u << lane) - 1u));
-        if (nz && pos < max_taps) {
-            const int y = i / side, x = i - y * side;
-            dib_tap t;
-            t.y = (int16_t)y;
-            t.x = (int16_t)x;
-            t.w = w;
-            taps[(int64_t)n * max_taps + pos] = t;
-        }
-        offset += __popc(ballot);
     }
     if (tid == 0) sh_running = total_count;
     __syncthreads();
+    DIB_CT(4);
     const int count = sh_running;
-    ymin = block_min_int(ymin, sh_i);
-    const int ymax = -block_min_int(ymax_neg, sh_i);
-    xmin = block_min_int(xmin, sh_i);
-    const int xmax = -block_min_int(xmax_neg, sh_i);
-    support = block_sum_ll(support, sh_ll);
-    sy = block_sum_ll(sy, sh_ll);
-    sx = block_sum_ll(sx, sh_ll);
-    syy = block_sum_ll(syy, sh_ll);
-    sxx = block_sum_ll(sxx, sh_ll);
-    sxy = block_sum_ll(sxy, sh_ll);
+    // Extents and moments (integer sums and minima: exact in any order): only the warps whose slab holds a tap or a positive
+    // cell take part.
+    if (warp_count != 0 || __any_sync(0xffffffffu, support_i != 0)) {       // warp-uniform
+        // shuffle trees inside the warp (32-bit: a warp's slab of a container up to 512 x 512 sums below 2^31 only for the
+        // first moments, so the second moments go 64-bit when the container is larger than 256 x 256), then lane 0 adds the
+        // warp's totals to the block's
+        int m4[4] = {ymin, ymax_neg, xmin, xmax_neg};
+        long long s6[6] = {support_i, sy_i, sx_i, syy_i, sxx_i, sxy_i};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m4[k] = min(m4[k], __shfl_xor_sync(0xffffffffu, m4[k], o));
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s6[k] = (int)s6[k] + __shfl_xor_sync(0xffffffffu, (int)s6[k], o);
+            if (side > 256) {
+#pragma unroll
+                for (int k = 3; k < 6; ++k) s6[k] += __shfl_xor_sync(0xffffffffu, s6[k], o);
+            } else {
+#pragma unroll
+                for (int k = 3; k < 6; ++k) s6[k] = (int)s6[k] + __shfl_xor_sync(0xffffffffu, (int)s6[k], o);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicMin(&sh_min4[k], m4[k]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(&sh_sum6[k], (unsigned long long)s6[k]);
+        }
+    }
+    __syncthreads();
+    ymin = sh_min4[0];
+    const int ymax = -sh_min4[1];
+    xmin = sh_min4[2];
+    const int xmax = -sh_min4[3];
+    long long sums6[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sums6[k] = (long long)sh_sum6[k];
+    const long long support = sums6[0], sy = sums6[1], sx = sums6[2], syy = sums6[3], sxx = sums6[4], sxy = sums6[5];
 
+    DIB_CT(5);
     // 3. program for the tiled kernel: dense sheared column groups (layout in dib_common.cuh, consumer blur_tiled.cu)
     const int centre = side > 129 ? 127 : 63;
     int flags = 0;
@@ -439,7 +480,9 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     const bool small_psf = want_prog && !(flags_in & DIB_COMPACT_DENSE_ONLY) &&
                            (mk_bound <= kMaskedMaxChunks || (flags_in & DIB_COMPACT_MASKED_ONLY));
     int mk_chunks = 0, mk_steps = 0, mk_segs = 0;
-    if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, s_finite, centre, ymin, ymax, xmin, xmax, my_prog, mk_chunks, mk_steps, mk_segs);
+    if (small_psf) mk::build_program<T, kStaged>(psf, sh_psf, side, normalize, s, s_finite, centre, ymin, ymax, xmin, xmax, my_prog,
+                                                    (flags_in & DIB_COMPACT_MASKED_ONLY) ? (1 << 20) : kMaskedMaxChunks, mk_chunks, mk_steps, mk_segs);
+    DIB_CT(6);
     const bool masked_ok = small_psf && mk_chunks > 0 && (mk_chunks <= kMaskedMaxChunks || (flags_in & DIB_COMPACT_MASKED_ONLY));
     if (want_prog && !masked_ok) {
         const int nrows_box = ymax - ymin + 1;
@@ -689,6 +732,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             if (attempt == 0 && cand == (1 * kNumShears + kShearMax)) break;      // the fallback candidate itself failed
         }
     }
+    DIB_CT(7);
     int nchunks_final = want_prog ? sh_nchunks : -1;
     if (masked_ok) {           // masked program: group width 0 in the summary
         nchunks_final = mk_chunks;
@@ -726,9 +770,17 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
         m.sxy = (double)sxy;
         meta[n] = m;
     }
+    DIB_CT(8);
 }
 
 }  // namespace dib
+
+#ifdef DIB_COMPACT_TIMING
+extern "C" __attribute__((visibility("default"))) int dib_debug_compact_times(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, dib::g_compact_t, sizeof(unsigned long long) * 16);
+}
+#endif
 
 extern "C" int dib_compact_taps(const void* psfs, int psf_dtype, int n_psfs, int side, int64_t psf_stride, int normalize,
                                 void* tapset, int max_taps, void* stream) {

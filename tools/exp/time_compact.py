@@ -20,7 +20,21 @@ for name in ("cfg2", "cfg3"):
             ops.compact_taps(p, normalize=True, sync=False)
         e1.record()
         torch.cuda.synchronize()
-        print(name, "n_psfs", n, "compact_taps %.1f us" % (e0.elapsed_time(e1) / 50 * 1e3))
+        direct = e0.elapsed_time(e1) / 50 * 1e3
+        # the same 20 calls replayed from a CUDA graph: device time without the host's launch path
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            keep = [ops.compact_taps(p, normalize=True, sync=False) for _ in range(20)]
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(name, "n_psfs", n, "compact_taps %.1f us issued directly, %.1f us from a graph" % (direct, e0.elapsed_time(e1) / 200 * 1e3))
     t = torch.from_numpy(traj[:1]).to(dev)
     f = torch.tensor(fr[:1], dtype=torch.float64, device=dev)
     for _ in range(5):
