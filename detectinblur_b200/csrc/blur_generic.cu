@@ -54,15 +54,17 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
         const int kind = psf_program_kind(p.meta[im.psf_index]);
         if (sizeof(T) == 2 ? kind == 1 : kind != 0) return;      // half images: only the masked kernel has a half path
     }
-    const int64_t pix = (int64_t)blockIdx.x * kGenericThreads + threadIdx.x;
-    if (pix >= (int64_t)im.H * im.W) return;
-    const int i = (int)(pix / im.W), j = (int)(pix - (int64_t)i * im.W);
     int count = 0;
     const dib_tap* taps = nullptr;
     if (im.psf_index >= 0) {
         count = min(p.meta[im.psf_index].count, p.max_taps);
         taps = p.taps + (int64_t)im.psf_index * p.max_taps;
     }
+    // grid-stride over the image's pixels: the grid is bounded (a few CTAs per SM and image), so a device-planned launch
+    // whose images all belong to the tiled kernels retires ~2 k CTAs instead of one per 256 pixels
+    const int64_t npix = (int64_t)im.H * im.W;
+    for (int64_t pix = (int64_t)blockIdx.x * kGenericThreads + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * kGenericThreads) {
+    const int i = (int)(pix / im.W), j = (int)(pix - (int64_t)i * im.W);
     for (int c0 = 0; c0 < im.C; c0 += kChanChunk) {
         const int nc = min(kChanChunk, im.C - c0);
         float acc[kChanChunk];
@@ -115,6 +117,7 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
             }
         }
     }
+    }
 }
 
 // Launch helper used by dib_blur_batch (blur_api.cu).
@@ -138,7 +141,16 @@ int launch_generic(const dib_image* images, int n_images, const dib_tap* taps, c
     p.philox_offset = offset;
     p.skip_mask = skip_mask;
     p.planned_mask = planned_mask;
-    dim3 grid((unsigned)((max_pix + kGenericThreads - 1) / kGenericThreads), (unsigned)n_images);
+    static thread_local int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        DIB_CUDA(cudaGetDevice(&dev));
+        DIB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // two full waves of resident CTAs (8 of 256 threads per SM) shared by the images; never more than the pixels need
+    const int64_t blocks_needed = (max_pix + kGenericThreads - 1) / kGenericThreads;
+    const int64_t blocks_cap = ((int64_t)sm_count * 16 + n_images - 1) / n_images;
+    dim3 grid((unsigned)(blocks_needed < blocks_cap ? blocks_needed : blocks_cap), (unsigned)n_images);
     if (io_dtype == DIB_F32)
         blur_generic_kernel<float><<<grid, kGenericThreads, 0, st>>>(p);
     else

@@ -276,11 +276,49 @@ __device__ __forceinline__ StageSmem stage_smem(uint8_t* base, int b) {
     return s;
 }
 
-__device__ __forceinline__ void decode_tile(const TiledParams& p, int tile, Stage& st) {
+// Device-planned launches (DIB_ALGO_DEVICE_PLAN): first tile of every image in the ticket sequence, decided from the PSF
+// summaries (warp 0, one lane per image, before the kernel's first block barrier).  Images of the other kernels get an
+// empty range, so a launch that owns nothing ends after this prologue instead of drawing a ticket per foreign tile.
+// Host-planned launches keep reading the host's first_tile from the kernel parameters, image by image and only as far as
+// the tile at hand needs (a lane-per-image read of the parameters costs 32 serialised constant-cache misses up front).
+__device__ __forceinline__ void tile_table(const TiledParams& p, int my_kind, int* first) {
+    if (p.meta_dev != nullptr && threadIdx.x < 32) {
+        const int n = threadIdx.x;
+        int cnt = 0;
+        if (n < p.n_images) {
+            const TiledImage& im = p.img[n];
+            cnt = im.tiles_x * im.tiles_y * im.C;
+            if (p.meta_dev != nullptr) {
+                const dib_psf_meta* m = p.meta_dev + im.psf_index;
+                const int4 a = __ldg(reinterpret_cast<const int4*>(m));
+                const int4 b = __ldg(reinterpret_cast<const int4*>(m) + 1);
+                const int2 c = __ldg(reinterpret_cast<const int2*>(m) + 4);
+                dib_psf_meta mm;
+                mm.count = a.x; mm.prog_chunks = b.y; mm.flags = b.w; mm.prog_group_w = (int16_t)(c.y & 0xffff);
+                if (psf_program_kind(mm) != my_kind) cnt = 0;
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (n >= o) incl += t;
+        }
+        first[n] = incl - cnt;
+        if (n == 31) first[DIB_MAX_BATCH] = incl;
+    }
+}
+
+// `first`: shared-memory table of the first tile of every image, first[DIB_MAX_BATCH] = all tiles (tile_table above), or null
+__device__ __forceinline__ void decode_tile(const TiledParams& p, const int* first, int tile, Stage& st) {
     int n = 0;
-    while (n + 1 < p.n_images && tile >= p.img[n + 1].first_tile) ++n;
+    if (first != nullptr) {
+        while (n + 1 < p.n_images && tile >= first[n + 1]) ++n;
+    } else {
+        while (n + 1 < p.n_images && tile >= p.img[n + 1].first_tile) ++n;
+    }
     const TiledImage& im = p.img[n];
-    const int local = tile - im.first_tile;
+    const int local = tile - (first != nullptr ? first[n] : im.first_tile);
     const int per_ch = im.tiles_x * im.tiles_y;
     st.img = n;
     st.ch = local / per_ch;
@@ -318,14 +356,14 @@ __device__ __forceinline__ ChunkRec load_chunk_rec(const TiledParams& p, int img
 // Hand the producer group its next tile.  Thread 0 of the group takes a ticket from the global counter and shares
 // it through shared memory; the two slots alternate so one named barrier per fetch is enough.
 constexpr unsigned kNoTicket = 0xffffffffu;
-__device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int& nfetch, int pt, unsigned pre = kNoTicket) {
+__device__ __forceinline__ int fetch_tile(const TiledParams& p, const int* first, int* slots, int& nfetch, int pt, unsigned pre = kNoTicket) {
     int* slot = slots + (nfetch & 1);
     if (pt == 0) {
         // the first tile of a CTA is its block index (no round trip to the counter before the first load can go out);
         // tickets from the counter follow after the gridDim.x tiles handed out that way.  `pre`: a ticket thread 0 drew
         // earlier (the atomic's round trip then overlaps the work in between)
         const unsigned t = nfetch == 0 ? blockIdx.x : gridDim.x + (pre != kNoTicket ? pre : atomicAdd(&p.sched->next_tile, 1u));
-        *slot = t < (unsigned)p.total_tiles ? (int)t : -1;
+        *slot = t < (unsigned)(first != nullptr ? first[DIB_MAX_BATCH] : p.total_tiles) ? (int)t : -1;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
     ++nfetch;
@@ -333,8 +371,8 @@ __device__ __forceinline__ int fetch_tile(const TiledParams& p, int* slots, int&
 }
 
 // successor of a stage: next chunk of the same tile, else chunk 0 of the next tile the scheduler hands out
-__device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cur, Stage& nx, int* slots, int& nfetch, int pt,
-                                           unsigned pre = kNoTicket) {
+__device__ __forceinline__ void next_stage(const TiledParams& p, const int* first, const Stage& cur, Stage& nx, int* slots, int& nfetch,
+                                           int pt, unsigned pre = kNoTicket) {
     if (cur.tile < 0) {
         nx.tile = -1;
         return;
@@ -344,11 +382,11 @@ __device__ __forceinline__ void next_stage(const TiledParams& p, const Stage& cu
         nx.chunk = cur.chunk + 1;
     } else {
         do {        // device-planned launches: tiles of images that belong to another kernel are skipped
-            nx.tile = fetch_tile(p, slots, nfetch, pt, pre);
+            nx.tile = fetch_tile(p, first, slots, nfetch, pt, pre);
             pre = kNoTicket;
             if (nx.tile < 0) return;
             nx.chunk = 0;
-            decode_tile(p, nx.tile, nx);
+            decode_tile(p, first, nx.tile, nx);
         } while (nx.nchunks == 0);
     }
     nx.rec = load_chunk_rec(p, nx.img, nx.chunk);
@@ -981,6 +1019,9 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
     if (!p.overlap_prev) asm volatile("griddepcontrol.wait;" ::: "memory");
     DIB_TRACE_EVENT(63, 0);
 
+    __shared__ int s_first_tab[DIB_MAX_BATCH + 1];
+    const int* s_first = p.meta_dev != nullptr ? s_first_tab : nullptr;
+    tile_table(p, 1, s_first_tab);
     if (threadIdx.x == 0) {
         // float: per producer thread one arrive.expect_tx + one cp.async arrive; half: one plain arrive after widening
         mbar_init(&full[0], (kHalf ? 1 : 2) * kProducerWarps * 32);
@@ -1007,15 +1048,15 @@ __global__ void __launch_bounds__(kThreads, 1) blur_masked_kernel(const __grid_c
         unsigned pre_ticket = kNoTicket;
         cur.chunk = 0;
         do {        // (device-planned launches skip the tiles of images that belong to another kernel)
-            cur.tile = fetch_tile(p, tile_slots, nfetch, pt);
+            cur.tile = fetch_tile(p, s_first, tile_slots, nfetch, pt);
             if (cur.tile < 0) break;
-            decode_tile(p, cur.tile, cur);
+            decode_tile(p, s_first, cur.tile, cur);
         } while (cur.nchunks == 0);
         if (cur.tile >= 0) cur.rec = load_chunk_rec(p, cur.img, 0);
         for (int n = 0;; ++n) {
             const int b = n & 1;
             DIB_TRACE_EVENT(15, n);
-            next_stage(p, cur, nxt, tile_slots, nfetch, pt, pre_ticket);     // its chunk record is in flight during the issue below
+            next_stage(p, s_first, cur, nxt, tile_slots, nfetch, pt, pre_ticket);     // its chunk record is in flight during the issue below
             pre_ticket = kNoTicket;
             // half path: the producers are busy for the whole stage (they widen the rows), so the ticket the NEXT call of
             // next_stage will need is drawn now and its round trip to the counter hides behind this stage's work
