@@ -52,8 +52,33 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, float a, flo
 
 // uint8 <-> float image planes, four pixels per thread.  Rows may be pitched on the float side (the blur's results are
 // [:, :, :W] views of row-aligned buffers); the uint8 side is dense.
+// The 256 possible results of byte / 255 (IEEE division in fp32, what torchvision's to_tensor computes) are tabulated once
+// per CTA: a lookup per pixel instead of a division.
 template <typename F>
-__global__ void u8_to_float_kernel(const uint8_t* __restrict__ src, F* __restrict__ dst, int64_t rows, int W, int64_t dst_pitch) {
+__global__ void __launch_bounds__(256) u8_to_float_kernel(const uint8_t* __restrict__ src, F* __restrict__ dst, int64_t rows, int W,
+                                                          int64_t dst_pitch) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+    __syncthreads();
+    if (dst_pitch == W && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (reinterpret_cast<uintptr_t>(dst) & (4 * sizeof(F) - 1)) == 0) {
+        // dense on both sides: the planes are one flat array -- four bytes in, four values out per thread, all vector accesses
+        const int64_t total = rows * W, nq = total >> 2;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+            const uchar4 b = reinterpret_cast<const uchar4*>(src)[q];
+            const float4 v = make_float4(lut[b.x], lut[b.y], lut[b.z], lut[b.w]);
+            if constexpr (sizeof(F) == 4) {
+                reinterpret_cast<float4*>(dst)[q] = v;
+            } else {
+                __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+                uint2 o;
+                o.x = *reinterpret_cast<unsigned*>(&lo);
+                o.y = *reinterpret_cast<unsigned*>(&hi);
+                reinterpret_cast<uint2*>(dst)[q] = o;
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (int)(total & 3)) dst[(nq << 2) + threadIdx.x] = (F)lut[src[(nq << 2) + threadIdx.x]];
+        return;
+    }
     const int quads = (W + 3) >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * quads; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / quads;
@@ -62,7 +87,7 @@ __global__ void u8_to_float_kernel(const uint8_t* __restrict__ src, F* __restric
         F* d = dst + r * dst_pitch + x0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            if (x0 + j < W) d[j] = (F)__fdiv_rn((float)s[j], 255.0f);      // torchvision's to_tensor: byte / 255 in fp32
+            if (x0 + j < W) d[j] = (F)lut[s[j]];
     }
 }
 template <typename F>

@@ -204,6 +204,11 @@ def test_u8_conversions(dib):
     ref = u8.cpu().float().div(255)
     assert torch.equal(f.cpu(), ref)
     assert torch.equal(ops.u8_to_float(u8, dtype=torch.float16).cpu(), ref.half())
+    into = torch.zeros((2, 3, 37, 104)).cuda()[..., :101]                   # pitched destination rows: the row-by-row path
+    ops.u8_to_float(u8, out=into)
+    assert torch.equal(into.cpu(), ref)
+    odd = u8.reshape(-1)[1:1 + 4 * 1000].reshape(4, 1000)                    # source not 4-byte aligned: row-by-row path again
+    assert torch.equal(ops.u8_to_float(odd).cpu(), odd.cpu().float().div(255))
     x = torch.rand((3, 50, 1333), generator=g).cuda() * 1.2 - 0.1
     pitched = torch.zeros((3, 50, 1336)).cuda()[:, :, :1333]
     pitched.copy_(x)
