@@ -75,22 +75,33 @@ __host__ __device__ constexpr int step_cost(int G) {
 __host__ __device__ constexpr int fill_cost(int G) { return 4 * (kRows - 1) * (kCC + G - 1) + 60; }
 constexpr int kChunkCost = 250;
 
-// first set bit at position >= from in a 128-bit mask (4 words, bit y of word y >> 5), or -1
-__device__ inline int mask_first_from(const unsigned* m, int from) {
-    for (int k = max(from, 0) >> 5; k < 4; ++k) {
-        unsigned w = m[k];
+// 128-bit row masks (bit y of word y >> 5) travel as uint4 VALUES: with pointers to thread-local arrays the dynamic word
+// index put them in local memory, and the single threads that walk the bands spent most of their time there.
+__device__ __forceinline__ unsigned mask_word(const uint4& m, int k) { return k == 0 ? m.x : k == 1 ? m.y : k == 2 ? m.z : m.w; }
+__device__ __forceinline__ uint4 mask_load(const unsigned* p) { return make_uint4(p[0], p[1], p[2], p[3]); }
+
+// first set bit at position >= from, or -1
+__device__ __forceinline__ int mask_first_from(const uint4& m, int from) {
+    from = max(from, 0);
+    int r = -1;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        unsigned w = mask_word(m, k);
         if (k == (from >> 5)) w &= 0xffffffffu << (from & 31);
-        if (w) return k * 32 + __ffs(w) - 1;
+        if (k < (from >> 5)) w = 0u;
+        if (w) r = k * 32 + __ffs(w) - 1;
     }
-    return -1;
+    return r;
 }
 
 // first and last set bit within [y0, y1] (f = -1 when none)
-__device__ inline void mask_range_first_last(const unsigned* m, int y0, int y1, int& f, int& l) {
+__device__ __forceinline__ void mask_range_first_last(const uint4& m, int y0, int y1, int& f, int& l) {
     f = -1;
     l = -1;
-    for (int k = y0 >> 5; k <= (y1 >> 5) && k < 4; ++k) {
-        unsigned w = m[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned w = mask_word(m, k);
+        if (k < (y0 >> 5) || k > (y1 >> 5)) w = 0u;
         if (k == (y0 >> 5)) w &= 0xffffffffu << (y0 & 31);
         if (k == (y1 >> 5)) w &= 0xffffffffu >> (31 - (y1 & 31));
         if (w) {
@@ -160,9 +171,11 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
     const int nbands = (ngroups + kChunkGroups - 1) / kChunkGroups;
     if (tid < nbands) {
         const int g0 = tid * kChunkGroups, g1 = min(g0 + kChunkGroups, ngroups);
-        unsigned band[4] = {0u, 0u, 0u, 0u};
-        for (int g = g0; g < g1; ++g)
-            for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
+        uint4 band = make_uint4(0u, 0u, 0u, 0u);
+        for (int g = g0; g < g1; ++g) {
+            const uint4 o = mask_load(&sh_occ[g * 4]);
+            band.x |= o.x; band.y |= o.y; band.z |= o.z; band.w |= o.w;
+        }
         int cursor = ymin, nb = 0;
         while (nb < kBandMaxChunks) {
             int y0 = mask_first_from(band, cursor);
@@ -172,7 +185,7 @@ __device__ void build_program(const T* psf, const float* sh_psf, int side, int n
             int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
             for (int g = g0; g < g1; ++g) {
                 int f, l;
-                mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
+                mask_range_first_last(mask_load(&sh_occ[g * 4]), y0, y1, f, l);
                 if (f < 0) continue;
                 SegRec sg;
                 sg.dx0 = (int16_t)(xmin + g * kGroupW - centre);
@@ -298,7 +311,8 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
     __shared__ int sh_band_count[kMaxBands], sh_band_base[kMaxBands];
     __shared__ int sh_first[kNumCand][kMaxGroups], sh_last[kNumCand][kMaxGroups];
     __shared__ int sh_xpmin[kNumShears], sh_xpmax[kNumShears];
-    __shared__ unsigned long long sh_cost[kNumCand];
+    __shared__ unsigned int sh_cost[kNumCand];      // modelled cycles (< 2^22 per candidate; 2^30 marks "does not fit"): 32-bit
+                                                    // shared atomics are native, 64-bit ones are CAS loops that crawl under contention
     __shared__ int sh_nchunks, sh_nsegs, sh_total_steps, sh_choice;
 
     DIB_CT(0);
@@ -492,12 +506,13 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             sh_xpmin[tid] = 1 << 20;
             sh_xpmax[tid] = -(1 << 20);
         }
-        if (tid < kNumCand) sh_cost[tid] = 0ull;
+        if (tid < kNumCand) sh_cost[tid] = 0u;
         for (int k = tid; k < kNumCand * kMaxGroups; k += kCompactThreads) {
             (&sh_first[0][0])[k] = 1 << 20;
             (&sh_last[0][0])[k] = -1;
         }
         __syncthreads();
+        DIB_CT(9);
         const int box_lo = ymin * side, box_hi = (ymax + 1) * side;       // the support's rows only
         for (int i = box_lo + tid; i < box_hi; i += kCompactThreads) {
             const float v = psf_cell<T, kStaged>(psf, sh_psf, i);
@@ -533,22 +548,23 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             }
         }
         __syncthreads();
+        DIB_CT(10);
         for (int k = tid; k < kNumCand * kMaxGroups; k += kCompactThreads) {
             const int cand = k / kMaxGroups, g = k - cand * kMaxGroups;
             const int gi = cand / kNumShears, q = cand - gi * kNumShears, G = 2 << gi;
             const int ngroups = ((sh_xpmax[q] - sh_xpmin[q]) >> (gi + 1)) + 1;
-            unsigned long long c = 0ull;
+            unsigned int c = 0u;
             if (ngroups > kMaxGroups) {
-                c = g == 0 ? (1ull << 40) : 0ull;                    // candidate does not fit the builder's tables
+                c = g == 0 ? (1u << 30) : 0u;                        // candidate does not fit the builder's tables
             } else if (g < ngroups) {
                 const int f = sh_first[cand][g], l = sh_last[cand][g];
                 if (l >= f) {
                     const int span = l - f + 1;
-                    c = (unsigned long long)(span * step_cost(G) + ((span + kChunkTapRows - 1) / kChunkTapRows) * fill_cost(G));
+                    c = (unsigned int)(span * step_cost(G) + ((span + kChunkTapRows - 1) / kChunkTapRows) * fill_cost(G));
                 }
                 if (g == 0) {       // staging cost: bands x row windows
                     const int nb = band_cols(q - kShearMax) / G;
-                    c += (unsigned long long)(((ngroups + nb - 1) / nb) * ((nrows_box + kChunkTapRows - 1) / kChunkTapRows) * kChunkCost);
+                    c += (unsigned int)(((ngroups + nb - 1) / nb) * ((nrows_box + kChunkTapRows - 1) / kChunkTapRows) * kChunkCost);
                 }
             }
             if (c) atomicAdd(&sh_cost[cand], c);
@@ -561,6 +577,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
             sh_choice = bestc;
         }
         __syncthreads();
+        DIB_CT(11);
         // 3b-3d. build with the chosen candidate; if it overflows a table, once more with unsheared groups of 4
         for (int attempt = 0; attempt < 2; ++attempt) {
             const int cand = attempt == 0 ? sh_choice : (1 * kNumShears + kShearMax);
@@ -590,14 +607,17 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                     if (any) atomicOr(&sh_occ[g * 4 + (y >> 5)], 1u << (y & 31));
                 }
                 __syncthreads();
+                DIB_CT(12);
                 // one thread per band walks the band's rows in windows of kChunkTapRows: pass 0 counts the chunks, pass 1
                 // (after a prefix sum over the bands) writes chunk and segment records
                 for (int pass = 0; pass < 2; ++pass) {
                     if (tid < nbands) {
                         const int g0 = tid * nb, g1 = min(g0 + nb, ngroups);
-                        unsigned band[4] = {0u, 0u, 0u, 0u};
-                        for (int g = g0; g < g1; ++g)
-                            for (int k = 0; k < 4; ++k) band[k] |= sh_occ[g * 4 + k];
+                        uint4 band = make_uint4(0u, 0u, 0u, 0u);
+                        for (int g = g0; g < g1; ++g) {
+                            const uint4 o = mask_load(&sh_occ[g * 4]);
+                            band.x |= o.x; band.y |= o.y; band.z |= o.z; band.w |= o.w;
+                        }
                         int cursor = ymin, nbc = 0;
                         const int base = pass ? sh_band_base[tid] : 0;
                         // rows of the band are cut into windows of equal height (not kChunkTapRows, kChunkTapRows, ...,
@@ -616,7 +636,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                                 int nseg = 0, lo = 1 << 20, hi = -(1 << 20), xlo = 1 << 20, xhi = -(1 << 20);
                                 for (int g = g0; g < g1; ++g) {
                                     int f, l;
-                                    mask_range_first_last(&sh_occ[g * 4], y0, y1, f, l);
+                                    mask_range_first_last(mask_load(&sh_occ[g * 4]), y0, y1, f, l);
                                     if (f < 0) continue;
                                     SegRec sg;
                                     const int d0 = xp0 + g * G + shear * (f - ymin) - centre, d1 = d0 + shear * (l - f);
@@ -664,6 +684,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                 sh_nchunks = -1;
             }
             __syncthreads();
+            DIB_CT(13);
             int nchunks = sh_nchunks;
             // offsets: weight vectors of a chunk's segments are laid out back to back
             if (nchunks > 0) {
@@ -697,6 +718,7 @@ compact_taps_kernel(const T* __restrict__ psfs, int side, int64_t psf_stride, in
                 nchunks = sh_nchunks;
             }
             if (nchunks > 0) {
+                DIB_CT(14);
                 // write chunk records, segment records and weight vectors
                 for (int k = tid; k < nchunks; k += kCompactThreads) out_chunks[k] = sh_chunks[k];
                 for (int ci = 0; ci < nchunks; ++ci) {

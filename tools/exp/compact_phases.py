@@ -22,4 +22,8 @@ for name in ("cfg2", "cfg3"):
         buf = (ctypes.c_uint64 * 16)()
         fn(buf)
         t = list(buf)[:9]
+        d = list(buf)[9:15]
+        if d[0] > t[6]:
+            print("   dense build: init %d, ranking passes %d, cost + choice %d, occupancy %d, band walks %d, offsets %d, records + weights %d" % (
+                d[0] - t[6], d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], t[7] - d[5]))
         print(name, "psf", first, "total cycles", t[8] - t[0], {names[k]: t[k + 1] - t[k] for k in range(8)})
