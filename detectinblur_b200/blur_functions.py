@@ -71,7 +71,7 @@ class BlurPlan(object):
         has already vacated instead of waiting for its last tile.  Chunks of one oversized batch always overlap."""
         global _launch_count
         ts = self.tapset
-        with torch.cuda.device(self.device):
+        with psf_ops._on_device(self.device):
             stream = psf_ops._stream_ptr(self.device)
             for lo in range(0, self.n, _lib.MAX_BATCH):
                 cnt = min(_lib.MAX_BATCH, self.n - lo)

@@ -103,7 +103,7 @@ def resize_normalize_batch(images, min_size, max_size, means=None, stds=None, si
     C = int(images[0].shape[0])
     batch = torch.empty((n, C, hp, wp), dtype=dtype, device=dev)
     launches = ctypes.c_int(0)
-    with torch.cuda.device(dev):
+    with psf_ops._on_device(dev):
         stream = psf_ops._stream_ptr(dev)
         for lo in range(0, n, _lib.MAX_BATCH):
             cnt = min(_lib.MAX_BATCH, n - lo)

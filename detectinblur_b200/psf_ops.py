@@ -12,6 +12,8 @@ import ctypes
 import math
 import os
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -20,7 +22,25 @@ from . import _lib
 _TORCH_TO_DIB = {torch.float32: _lib.DIB_F32, torch.float16: _lib.DIB_F16, torch.float64: _lib.DIB_F64}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def _on_device(device):
+    """Context that makes ``device`` current for a C-ABI call; nothing to do (and ~10 us less per call) when it already is."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
+
+
 def _stream_ptr(device):
+    """The caller's current CUDA stream on ``device`` as a raw pointer.  torch.cuda.current_stream() builds a Stream object
+    and resolves the device three times (9 us per call, three calls per image in the batch-1 chain); the raw query is the
+    same value in 0.3 us."""
+    if _raw_stream is not None:
+        idx = device.index
+        return ctypes.c_void_p(_raw_stream(idx if idx is not None else torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -112,7 +132,7 @@ def compact_taps(psfs, normalize, max_taps=1024, dense_only=None, sync=True):
     n, side = int(psfs.shape[0]), int(psfs.shape[1])
     lay = _lib.tapset_layout(n, max_taps)
     buf = torch.empty(lay.total_bytes, dtype=torch.uint8, device=psfs.device)
-    with torch.cuda.device(psfs.device):
+    with _on_device(psfs.device):
         _lib.check(_lib.lib.dib_compact_taps(ctypes.c_void_p(psfs.data_ptr()), _TORCH_TO_DIB[psfs.dtype], n, side,
                                              side * side, (1 if normalize else 0) | (2 if dense_only else 0) | (4 if os.environ.get("DIB_MASKED_ONLY", "0") not in ("0", "") else 0), ctypes.c_void_p(buf.data_ptr()),
                                              int(max_taps), _stream_ptr(psfs.device)))
@@ -166,7 +186,7 @@ def rasterize_psfs(trajectories, fractions, device, canvas=256, center=True, out
     out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
     offs = torch.empty((n, 2), dtype=torch.int32, device=device)
     scratch = torch.empty((n, canvas, canvas), dtype=torch.float64, device=device)
-    with torch.cuda.device(device):
+    with _on_device(device):
         _lib.check(_lib.lib.dib_rasterize_psf(ctypes.c_void_p(t_traj.data_ptr()), ctypes.c_void_p(t_fr.data_ptr()), n, iters,
                                               int(canvas), 1 if center else 0, int(out_side), ctypes.c_void_p(out.data_ptr()),
                                               _TORCH_TO_DIB[dtype], ctypes.c_void_p(offs.data_ptr()),
@@ -193,7 +213,7 @@ def generate_trajectories(n, expl, seed, device, first_index=0, canvas=256, iter
     idx = None
     if indices is not None:
         idx = torch.as_tensor(np.asarray(indices, dtype=np.int64).reshape(n), device=device)     # bit pattern of the uint64s
-    with torch.cuda.device(device):
+    with _on_device(device):
         _lib.check(_lib.lib.dib_generate_trajectories(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_index),
                                                       ctypes.c_void_p(idx.data_ptr()) if idx is not None else None, int(n), int(iters),
                                                       float(max_len), float(canvas), ctypes.c_void_p(ex.data_ptr()),
@@ -224,7 +244,7 @@ def unpack_psfs(packed_taps, offsets, device, crop_lo=64, out_side=128, dtype=to
     host[8 * (n + 1):8 * (n + 1) + 4 * len(packed_taps)] = packed_taps.view(np.uint8)
     dev_buf = stage.to(device, non_blocking=True)
     out = torch.empty((n, out_side, out_side), dtype=dtype, device=device)
-    with torch.cuda.device(device):
+    with _on_device(device):
         _lib.check(_lib.lib.dib_unpack_psfs(ctypes.c_void_p(dev_buf.data_ptr() + 8 * (n + 1)), ctypes.c_void_p(dev_buf.data_ptr()),
                                             n, int(crop_lo), int(out_side), ctypes.c_void_p(out.data_ptr()),
                                             _TORCH_TO_DIB[dtype], _stream_ptr(device)))
@@ -241,7 +261,7 @@ def checksum(tensor, out=None, accumulate=False):
     if out is None:
         out = torch.zeros(1, dtype=torch.int64, device=t.device)
         accumulate = False
-    with torch.cuda.device(t.device):
+    with _on_device(t.device):
         _lib.check(_lib.lib.dib_checksum(ctypes.c_void_p(t.data_ptr()), _TORCH_TO_DIB[t.dtype], t.numel(),
                                          ctypes.c_void_p(out.data_ptr()), 1 if accumulate else 0, _stream_ptr(t.device)))
     return out
@@ -258,7 +278,7 @@ def u8_to_float(images_u8, dtype=torch.float32, out=None):
     rows = src.numel() // W
     if out is None:
         out = torch.empty(src.shape, dtype=dtype, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on_device(src.device):
         _lib.check(_lib.lib.dib_u8_to_float(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()), _TORCH_TO_DIB[out.dtype],
                                             rows, W, out.stride(-2) if out.dim() > 1 else W, _stream_ptr(src.device)))
     return out
@@ -275,7 +295,7 @@ def float_to_u8(image, out=None):
         image = image.contiguous()
     if out is None:
         out = torch.empty((C, H, W), dtype=torch.uint8, device=image.device)
-    with torch.cuda.device(image.device):
+    with _on_device(image.device):
         _lib.check(_lib.lib.dib_float_to_u8(ctypes.c_void_p(image.data_ptr()), _TORCH_TO_DIB[image.dtype], ctypes.c_void_p(out.data_ptr()),
                                             C * H, W, image.stride(1), _stream_ptr(image.device)))
     return out
