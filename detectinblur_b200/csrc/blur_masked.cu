@@ -456,11 +456,14 @@ __device__ __forceinline__ void issue_stage(const TiledParams& p, const Stage& s
         // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels (4-byte cp.async each), or zeros in
         // zero-padding mode.  All producer threads share the (row, column) pairs; the row table tells where a row sits.
         asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
+        // (a chunk whose taps all point past the right edge of a last column tile stages no image column at all: cl >= W;
+        //  the mirrored columns then start at cl, not at the first column beyond the image)
+        const int rb = max(xb1, cl);
+        const int nleft = min(xa, cr + 1) - cl, ncols = nleft + cr + 1 - rb;
         const int total = nrows * ncols;
         for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
             const int r2 = idx / ncols, k = idx - r2 * ncols;
-            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
+            const int col = k < nleft ? cl + k : rb + (k - nleft);
             const int irow = rt + r2;
             float* d = sm.tile + sm.rowtab[r2] - cl + col;
             if (im.zero_pad) {
@@ -512,7 +515,9 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
             const uint32_t rowphase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) >> 1);       // in halves
             xa_al = xa + (int)((0u - (rowphase + (uint32_t)xa)) & 7u);
             xb_al = xb1 - (int)((rowphase + (uint32_t)xb1) & 7u);
-            if (xb_al <= xa_al) xa_al = xb_al = xa;
+            // no whole aligned group of 8 inside (a last column tile that holds few image columns: the span is then at most
+            // 7 + 7 elements): the first seven travel as the "head", the rest as the "tail" -- both are register arrays of 7
+            if (xb_al <= xa_al) xa_al = xb_al = min(xa + 7, xb1);
         }
         ro += (int)((uint32_t)(cl - xa_al) & 7u);       // skew: (xa_al - cl + skew) is a multiple of 8
         const uint32_t nb = (uint32_t)(xb_al - xa_al) * 2u;
@@ -596,12 +601,15 @@ __device__ __forceinline__ void issue_stage_half(const TiledParams& p, const Sta
         // border columns [cl, xa) and [xb1, cr] of every staged row: mirrored pixels, or zeros in zero-padding mode.  All
         // producer threads share the (row, column) pairs; the row table written above tells where each row sits.
         asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory");
-        const int nleft = xa - cl, ncols = nleft + cr + 1 - xb1;
+        // (a chunk whose taps all point past the right edge of a last column tile stages no image column at all: cl >= W;
+        //  the mirrored columns then start at cl, not at the first column beyond the image)
+        const int rb = max(xb1, cl);
+        const int nleft = min(xa, cr + 1) - cl, ncols = nleft + cr + 1 - rb;
         const int total = nrows * ncols;
 #pragma unroll 4
         for (int idx = pt; idx < total; idx += kProducerWarps * 32) {
             const int r2 = idx / ncols, k = idx - r2 * ncols;
-            const int col = k < nleft ? cl + k : xb1 + (k - nleft);
+            const int col = k < nleft ? cl + k : rb + (k - nleft);
             const int irow = rt + r2;
             float v = 0.0f;
             bool write = true;

@@ -440,12 +440,15 @@ __device__ __forceinline__ void finish_stage(const TiledParams& p, const Stage& 
         const int ncols = g.cr - g.cl + 1;
         if (cols_out) {
             const int xa = max(g.cl, 0), xb1 = min(g.cr, im.W - 1) + 1;          // in-image columns [xa, xb1)
-            const int nleft = xa - g.cl, nborder = nleft + g.cr + 1 - xb1;
+            // (a chunk whose taps all point past the right edge of a last column tile stages no image column: cl >= W; the
+            //  mirrored columns then start at cl, not at the first column beyond the image)
+            const int rb = max(xb1, g.cl);
+            const int nleft = min(xa, g.cr + 1) - g.cl, nborder = nleft + g.cr + 1 - rb;
             for (int r2 = top + pw; r2 < g.nrows - bot; r2 += kProducerWarps) {
                 const int skew = (g.skew0 + r2 * g.dskew) & 3;
                 const uint32_t row = tile + (uint32_t)r2 * kRowBytes + 4u * (uint32_t)(skew - g.cl);     // + 4 * col
                 for (int k = lane; k < nborder; k += 32) {
-                    const int col = k < nleft ? g.cl + k : xb1 + (k - nleft);
+                    const int col = k < nleft ? g.cl + k : rb + (k - nleft);
                     if (im.zero_pad) {
                         sts_f32(row + 4u * (uint32_t)col, 0.0f);
                     } else {

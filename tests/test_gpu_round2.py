@@ -329,3 +329,38 @@ def test_rasterizer_cluster_splits_are_bit_identical(dib, golden_dir, split, mon
             ref_cen = np.zeros(256 * 256)
             ref_cen[g["cen_idx_%d" % (k % n)]] = g["cen_val_%d" % (k % n)]
             assert np.array_equal(out[k], ref_cen.reshape(256, 256).astype(np.float16)[64:192, 64:192]), (count, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("width", [449, 450, 455, 897, 1345])
+def test_last_column_tile_a_few_pixels_wide(dib, dtype, width, monkeypatch):
+    """Found by tools/exp/stress_parity.py: when the last 448-column tile holds only a few image columns, (a) a half row's
+    staged span can be 8-14 elements without one 16-byte-aligned group (its ends then travel as two register arrays of 7),
+    and (b) a chunk whose taps all point right of the tile stages no image column at all (cl >= W: every staged column is a
+    mirrored one).  Both tiled kernels, reflect and zero padding, against the exact-order kernel."""
+    bf, ops = dib
+    from detectinblur_b200 import _lib
+    rng = np.random.default_rng(width)
+    np.random.seed(width)
+    psfs = []
+    for expl, frac in ((0.005, 1 / 5), (0.001, 1 / 2), (0.00005, 1), (0.00005, 1)):
+        p16, _ = po.stored_psf(expl, frac, np.random)
+        psfs.append(po.crop128(p16).astype(np.float32))
+    psfs = _cuda(np.stack(psfs)).to(dtype)
+    imgs = [_cuda(rng.random((c, 70 + 30 * k, width), dtype=np.float32)).to(dtype) for k, c in enumerate((1, 3, 2, 3))]
+    tol = 2e-2 if dtype == torch.float16 else 1e-5
+    for force in (None, "DIB_DENSE_ONLY", "DIB_MASKED_ONLY"):
+        if force is not None:
+            if dtype == torch.float16 and force == "DIB_DENSE_ONLY":
+                continue                                   # half images have no dense-kernel path
+            monkeypatch.setenv(force, "1")
+        ts = ops.compact_taps(psfs, normalize=True)
+        for pad in (None, _lib.PAD_ZERO128):
+            got = bf.blur_batch(imgs, ts, [0, 1, 2, 3], pad_mode=pad)
+            want = bf.blur_batch(imgs, ts, [0, 1, 2, 3], pad_mode=pad, exact=True)
+            for k in range(4):
+                err = float((got[k].float() - want[k].float()).abs().max())
+                assert err <= tol, (force, pad, k, err)
+        if force is not None:
+            monkeypatch.delenv(force)
