@@ -364,3 +364,31 @@ def test_last_column_tile_a_few_pixels_wide(dib, dtype, width, monkeypatch):
                 assert err <= tol, (force, pad, k, err)
         if force is not None:
             monkeypatch.delenv(force)
+
+
+def _load_tool(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", "exp", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("routing", [None, "DIB_DENSE_ONLY", "DIB_MASKED_ONLY"])
+def test_randomised_parity_stress(dib, routing, monkeypatch):
+    """A few seconds of tools/exp/stress_parity.py (random sizes / dtypes / pad modes / pitches / store paths / epilogues, PSFs
+    of every sweep cell, host- and device-planned): the tiled kernels against the exact-order kernel.  The tool found the two
+    last-column-tile bugs pinned above; it runs here so that the next one shows up in the suite."""
+    if routing:
+        monkeypatch.setenv(routing, "1")
+    msg = _load_tool("stress_parity").run(6.0, 101)
+    assert msg.startswith("ok")
+
+
+@pytest.mark.gpu
+def test_randomised_psf_stress(dib):
+    """A few seconds of tools/exp/stress_psf.py: synthetic PSFs (sparse sets, lines, blobs, rings, border taps, single taps) through
+    the compaction and both program builders -- exact-order kernel == numpy oracle bit for bit, tiled kernels <= 1e-5."""
+    msg = _load_tool("stress_psf").run(6.0, 202)
+    assert msg.startswith("ok")
