@@ -392,3 +392,12 @@ def test_randomised_psf_stress(dib):
     the compaction and both program builders -- exact-order kernel == numpy oracle bit for bit, tiled kernels <= 1e-5."""
     msg = _load_tool("stress_psf").run(6.0, 202)
     assert msg.startswith("ok")
+
+
+@pytest.mark.gpu
+def test_randomised_rasteriser_stress(dib):
+    """A few seconds of tools/exp/stress_raster.py: random walks (up to thousands of positive cells: the centroid list is flushed
+    in chunks), canvases 64 / 128 / 256, 37-4096 samples, fractions from one sample to 1, batch sizes that hit every cluster
+    split -- raw canvas, centring offsets and centred canvas equal the numpy oracle bit for bit (generate_PSF.py:31-123)."""
+    msg = _load_tool("stress_raster").run(5.0, 303)
+    assert msg.startswith("ok")
