@@ -12,8 +12,10 @@ print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); print(
 for e in d.get('extra',[]): print(json.dumps(e)[:300])
 "
 cat gpurun_out/time_compact.txt; cut -c1-300 gpurun_out/bench_ref.json
+if [ -n "$RECORD_NCU_FULL" ]; then
 # ncu --set full digests of the kernels whose code changed late in the round (read with tools/ncu_summary.py on the CPU box)
 ncu --set full --clock-control none --import-source on -k regex:"blur_masked_kernel" -s 6 -c 1 -o gpurun_out/prof_r2c_cfg2 python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --no-overlap > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"blur_masked_kernel" -s 6 -c 1 -o gpurun_out/prof_r2c_cfg2h python bench.py --workload cfg2h --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras --no-overlap > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"compact_taps" -s 3 -c 1 -o gpurun_out/prof_r2c_compact python tools/exp/time_compact.py > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
+fi
