@@ -401,3 +401,11 @@ def test_randomised_rasteriser_stress(dib):
     split -- raw canvas, centring offsets and centred canvas equal the numpy oracle bit for bit (generate_PSF.py:31-123)."""
     msg = _load_tool("stress_raster").run(5.0, 303)
     assert msg.startswith("ok")
+
+
+@pytest.mark.gpu
+def test_randomised_resize_stress(dib):
+    """A few seconds of tools/exp/stress_resize.py: random image sizes, size limits and per-image mean / std through the fused
+    normalize + resize + padded-batch kernel against the reference transform's own torch calls (net_transforms.py:112-249)."""
+    msg = _load_tool("stress_resize").run(4.0, 404)
+    assert msg.startswith("ok")
