@@ -61,7 +61,10 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh) {
 
 constexpr int kMaxGroups = 192;       // sheared groups of one PSF (support width + shear drift, in groups of 2)
 constexpr int kMaxBands = 64;
-constexpr int kMaskedMaxChunks = 4;      // PSFs whose masked program needs more chunks take the dense sheared kernel
+#ifndef DIB_MASKED_MAX_CHUNKS
+#define DIB_MASKED_MAX_CHUNKS 4
+#endif
+constexpr int kMaskedMaxChunks = DIB_MASKED_MAX_CHUNKS;      // PSFs whose masked program needs more chunks take the dense sheared kernel
 constexpr int kNumShears = 2 * kShearMax + 1;
 constexpr int kNumCand = 2 * kNumShears;          // group width 2 or 4 x shear -kShearMax .. kShearMax
 
