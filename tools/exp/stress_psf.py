@@ -1,5 +1,5 @@
 """Randomised stress of the tap compaction and the program builders with SYNTHETIC PSFs (random sparse sets, line segments,
-dense blobs, taps on the container's border rows / columns, single taps, all-zero), fp32 and fp16 PSFs, sides 128 / 65 / 129:
+dense blobs, taps on the container's border rows / columns, single taps, all-zero), fp32 and fp16 PSFs, sides 128 / 65 / 129 / 256 (the replicate-padded branch):
 exact-order kernel against the numpy oracle (bit for bit, fp32), tiled kernels against the exact-order kernel (<= 1e-5).
     python tools/exp/stress_psf.py [seconds] [seed]      (test infrastructure: imports oracle/)"""
 import os, random, sys, time
@@ -63,7 +63,7 @@ def run(budget=60.0, seed=0):
     stats = {"masked": 0, "dense": 0, "none": 0}
     worst = 0.0
     while time.time() - t0 < budget:
-        side = int(rng.choice([128, 128, 128, 65, 129]))
+        side = int(rng.choice([128, 128, 128, 65, 129, 256]))
         nb = int(rng.integers(1, 5))
         half_psf = rng.random() < 0.3
         psfs = np.stack([make_psf(side) for _ in range(nb)])
