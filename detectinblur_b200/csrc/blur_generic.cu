@@ -111,7 +111,20 @@ blur_generic_kernel(const __grid_constant__ GenericParams p) {
                             nz = philox_normal(p.philox_seed, p.philox_offset + (uint64_t)n,
                                                ((uint64_t)ch * im.H + i) * im.W + j);
                     }
-                    v = apply_epilogue_f32(v, e, nz);
+                    if constexpr (sizeof(T) == 2) {
+                        // half images: torch rounds to half after every elementwise operation (blur_functions.py:74:
+                        // randn * sd, + output, clamp; net_transforms.py:135-139: - mean, / std with half mean / std tensors)
+                        if (e.flags & DIB_EPI_NOISE) v = IoNum<T>::add(v, IoNum<T>::mul(nz, e.noise_sd));
+                        if (e.flags & DIB_EPI_CLAMP) v = fminf(fmaxf(v, 0.0f), 1.0f);
+                        if (e.flags & DIB_EPI_GAMMA) v = __half2float(__float2half_rn(powf(v, e.gamma)));
+                        if (e.flags & DIB_EPI_NORMALIZE) {
+                            const float mh = __half2float(__float2half_rn(e.mean)), sh = __half2float(__float2half_rn(e.std));
+                            v = __half2float(__float2half_rn(__fsub_rn(v, mh)));
+                            v = __half2float(__float2half_rn(__fdiv_rn(v, sh)));
+                        }
+                    } else {
+                        v = apply_epilogue_f32(v, e, nz);
+                    }
                 }
                 IoNum<T>::store(im.dst, o, v);
             }

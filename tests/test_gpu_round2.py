@@ -409,3 +409,13 @@ def test_randomised_resize_stress(dib):
     normalize + resize + padded-batch kernel against the reference transform's own torch calls (net_transforms.py:112-249)."""
     msg = _load_tool("stress_resize").run(4.0, 404)
     assert msg.startswith("ok")
+
+
+@pytest.mark.gpu
+def test_randomised_drop_in_against_the_reference_on_cuda(dib):
+    """A few seconds of tools/exp/stress_reference.py: random image lists, blurring flags, dtypes and the noise epilogue through
+    blur_image_list here and through the UNMODIFIED reference's blur_image_list on the same GPU (baseline/_ref) under the same
+    numpy / torch seeds -- exact-order path bit for bit (the tool found that the half-precision noise epilogue rounded once
+    where torch rounds after every operation), default path within 1e-5 / 2e-2."""
+    msg = _load_tool("stress_reference").run(6.0, 505)
+    assert msg.startswith("ok") or msg.startswith("skipped")
